@@ -1,0 +1,153 @@
+"""Adversarial batch builder for the parity tests (SURVEY.md section 8(c) classes).
+
+Test infrastructure: uses the oracle for point arithmetic.  Every class states the status the
+reference semantics give (0 Ok, 1 InvalidSignature, 2 InvalidPoint, 3 BytesError); the tests still
+compare the CUDA path against the oracle item by item, the expected code is a second check.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import c_oracle as co
+from oracle import jjs_oracle as o
+
+Q_BYTES = np.frombuffer(o.le32(o.Q), dtype=np.uint8)
+IDENTITY_ENC = o.point_to_bytes(o.IDENTITY)
+ORDER2_ENC = o.point_to_bytes((0, o.Q - 1))
+
+
+def torsion_points():
+    """Encodings of points of exact order 2, 4 and 8 (T = [r] * random curve point)."""
+    out = {}
+    v = 2
+    while len(out) < 3:
+        v += 1
+        enc = bytearray(o.le32(v))
+        p = co.point_decode(bytes(enc))
+        if p is None:
+            continue
+        t = co.point_mul(bytes(enc), o.R_ORDER)
+        order = 1
+        cur = t
+        while cur != IDENTITY_ENC:
+            cur = co.point_add(cur, t)
+            order += 1
+            assert order <= 8
+        if order == 8:
+            t8 = t
+            out[8] = t8
+            out[4] = co.point_add(t8, t8)
+            out[2] = co.point_add(out[4], out[4])
+    assert out[2] == ORDER2_ENC
+    return out
+
+
+_TORSION = None
+
+
+def torsion():
+    global _TORSION
+    if _TORSION is None:
+        _TORSION = torsion_points()
+    return _TORSION
+
+
+def off_curve_encoding(rng) -> bytes:
+    while True:
+        v = int.from_bytes(rng.bytes(32), "little") % o.Q
+        b = o.le32(v)
+        if co.point_decode(b) is None:
+            return b
+
+
+def noncanonical_v_encoding(rng) -> bytes:
+    """v in [q, 2^255): rejected by JubJubAffine::from_bytes."""
+    v = o.Q + int(rng.integers(0, 1 << 62))
+    assert v < (1 << 255)
+    b = bytearray(o.le32(v))
+    b[31] |= int(rng.integers(0, 2)) << 7
+    return bytes(b)
+
+
+# (name, expected status, which field it touches)
+POINT_CLASSES = [
+    ("off_curve", 3), ("v_ge_q", 3), ("identity", 2), ("order2", 2), ("plus_t2", 2), ("plus_t4", 2),
+    ("plus_t8", 2), ("zip216_identity", 3), ("zip216_order2", 3),
+]
+
+
+def tamper_point(enc: bytes, cls: str, rng) -> bytes:
+    t = torsion()
+    if cls == "off_curve":
+        return off_curve_encoding(rng)
+    if cls == "v_ge_q":
+        return noncanonical_v_encoding(rng)
+    if cls == "identity":
+        return IDENTITY_ENC
+    if cls == "order2":
+        return ORDER2_ENC
+    if cls in ("plus_t2", "plus_t4", "plus_t8"):
+        return co.point_add(enc, t[int(cls[-1])])
+    if cls == "zip216_identity":
+        b = bytearray(IDENTITY_ENC); b[31] |= 0x80; return bytes(b)
+    if cls == "zip216_order2":
+        b = bytearray(ORDER2_ENC); b[31] |= 0x80; return bytes(b)
+    raise ValueError(cls)
+
+
+def make_adversarial(kind: str, pk, sig, msg, seed: int, frac: float = 0.5):
+    """Tamper a fraction of a valid batch.  kind in {"single", "double", "vargen"}.
+
+    Returns (pk, sig, msg, expected_status, class_names).  Point fields: single pk[0:32], sig[32:64];
+    double pk[0:32], pk[32:64], sig[32:64], sig[64:96]; vargen pk[0:32] (key), pk[32:64] (generator),
+    sig[32:64].
+    """
+    rng = np.random.default_rng(seed)
+    pk, sig, msg = pk.copy(), sig.copy(), msg.copy()
+    n = msg.shape[0]
+    expected = np.zeros(n, dtype=np.uint8)
+    names = ["valid"] * n
+    pk_fields = {"single": [0], "double": [0, 32], "vargen": [0, 32]}[kind]
+    sig_fields = {"single": [32], "double": [32, 64], "vargen": [32]}[kind]
+    classes = []
+    for cname, st in POINT_CLASSES:
+        for f in pk_fields:
+            classes.append(("pk%d_%s" % (f, cname), st, ("pk", f, cname)))
+        for f in sig_fields:
+            classes.append(("sig%d_%s" % (f, cname), st, ("sig", f, cname)))
+    classes += [
+        ("u_tampered", 1, None), ("u_ge_r", 3, None), ("u_all_ff", 3, None), ("m_tampered", 1, None), ("m_ge_q", 3, None),
+        ("R_other_point", 1, None), ("R_sign_flip", 1, None), ("pk_other_key", 1, None),
+    ]
+    idx = rng.permutation(n)[: int(n * frac)]
+    for j, i in enumerate(idx):
+        name, st, spec = classes[j % len(classes)]
+        if spec is not None:
+            arr = pk if spec[0] == "pk" else sig
+            f = spec[1]
+            arr[i, f:f + 32] = np.frombuffer(tamper_point(arr[i, f:f + 32].tobytes(), spec[2], rng), dtype=np.uint8)
+        elif name == "u_tampered":
+            u = (int.from_bytes(sig[i, :32].tobytes(), "little") + 1 + int(rng.integers(0, 1 << 60))) % o.R_ORDER
+            sig[i, :32] = np.frombuffer(o.le32(u), dtype=np.uint8)
+        elif name == "u_ge_r":
+            u = o.R_ORDER + int(rng.integers(0, 1 << 60))
+            sig[i, :32] = np.frombuffer(o.le32(u), dtype=np.uint8)
+        elif name == "u_all_ff":
+            sig[i, :32] = 0xFF
+        elif name == "m_tampered":
+            m = (int.from_bytes(msg[i].tobytes(), "little") + 1) % o.Q
+            msg[i] = np.frombuffer(o.le32(m), dtype=np.uint8)
+        elif name == "m_ge_q":
+            msg[i] = np.frombuffer(o.le32(o.Q + int(rng.integers(0, 1 << 60))), dtype=np.uint8)
+        elif name == "R_other_point":
+            other = (i + 1) % n
+            sig[i, 32:64] = sig[other, 32:64] if names[other] == "valid" else pk[other, :32]
+            if not co.point_is_valid(sig[i, 32:64].tobytes()) == 1:
+                sig[i, 32:64] = np.frombuffer(o.point_to_bytes(o.G), dtype=np.uint8)
+        elif name == "R_sign_flip":
+            sig[i, 63] ^= 0x80
+        elif name == "pk_other_key":
+            pk[i, :32] = np.frombuffer(o.point_to_bytes(o.pmul(o.G, 1 + int(rng.integers(1, 1 << 30)))), dtype=np.uint8)
+        expected[i] = st
+        names[i] = name
+    return pk, sig, msg, expected, names
