@@ -1,0 +1,455 @@
+// JubJub (twisted Edwards, a = -1) group arithmetic, point decoding with a table-driven square root, and
+// the scalar-multiplication building blocks of the verify path, for sm_100a.
+//
+// Replaces what the reference reaches through dusk-jubjub: JubJubAffine::from_bytes / from_slice
+// (reference src/keys/public.rs:88, src/signatures.rs:114), `point * scalar`, `+`, projective `eq`
+// (src/keys/public.rs:128-130), is_torsion_free / is_on_curve / is_identity (src/keys/public.rs:159-164).
+#pragma once
+#include "consts.cuh"
+#include "fq.cuh"
+
+namespace jjs {
+
+JJS_HD void fq_load_const(fq& r, const uint32_t* c) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = c[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// large lookup tables living in global memory (device) or in the generated host arrays (hostsim)
+// ---------------------------------------------------------------------------------------------
+constexpr int FB_W = 8;                       // fixed-base window width (bits)
+constexpr int FB_WINDOWS = (252 + FB_W - 1) / FB_W;
+constexpr int FB_ENTRIES = 1 << FB_W;
+
+struct niels {  // affine Niels form of a fixed-base table entry: (v + u, v - u, 2 d u v)
+    fq ypx, ymx, t2d;
+};
+
+struct Tables {
+    const fq* root_tables;     // [6][256]  g^(-j 2^k) tables for the 2^32-torsion discrete log
+    const uint8_t* dlog_hash;  // [1 << JJS_DLOG_HASH_BITS]
+    const niels* fb_g;         // [FB_WINDOWS][FB_ENTRIES]  j * 2^(FB_W w) * G
+    const niels* fb_gn;        // same for G' (GENERATOR_NUMS_EXTENDED)
+};
+
+// ---------------------------------------------------------------------------------------------
+// points
+// ---------------------------------------------------------------------------------------------
+struct ext {  // extended coordinates, u = X/Z, v = Y/Z, T = XY/Z
+    fq X, Y, Z, T;
+};
+struct pniels {  // projective Niels form of a variable-base table entry: (Y + X, Y - X, 2 Z, 2 d T)
+    fq ypx, ymx, z2, t2d;
+};
+
+JJS_HD void ext_identity(ext& p) {
+    fq_zero(p.X);
+    fq_one(p.Y);
+    fq_one(p.Z);
+    fq_zero(p.T);
+}
+JJS_HD void ext_from_affine(ext& p, const fq& u, const fq& v) {
+    p.X = u;
+    p.Y = v;
+    fq_one(p.Z);
+    fq_mul(p.T, u, v);
+}
+// dbl-2008-hwcd with a = -1: 4S + 4M (3M when the T output is not needed)
+template <bool WANT_T>
+JJS_HD void ext_dbl(ext& r, const ext& p) {
+    fq a, b, c, e, f, g, h, t;
+    fq_sqr(a, p.X);
+    fq_sqr(b, p.Y);
+    fq_sqr(c, p.Z);
+    fq_dbl(c, c);
+    fq_add(t, p.X, p.Y);
+    fq_sqr(e, t);
+    fq_sub(e, e, a);
+    fq_sub(e, e, b);   // E = 2XY
+    fq_sub(g, b, a);   // G = D + B, D = -A
+    fq_sub(f, g, c);   // F = G - C
+    fq_add(h, a, b);
+    fq_neg(h, h);      // H = D - B = -(A + B)
+    fq_mul(r.X, e, f);
+    fq_mul(r.Y, g, h);
+    fq_mul(r.Z, f, g);
+    if (WANT_T) fq_mul(r.T, e, h);
+}
+// add-2008-hwcd-3 (a = -1, complete since d is a non-square): extended + projective Niels, 8M (7M without T)
+template <bool WANT_T>
+JJS_HD void ext_add_pniels(ext& r, const ext& p, const pniels& q) {
+    fq a, b, c, d, e, f, g, h, t;
+    fq_sub(t, p.Y, p.X);
+    fq_mul(a, t, q.ymx);
+    fq_add(t, p.Y, p.X);
+    fq_mul(b, t, q.ypx);
+    fq_mul(c, p.T, q.t2d);
+    fq_mul(d, p.Z, q.z2);
+    fq_sub(e, b, a);
+    fq_sub(f, d, c);
+    fq_add(g, d, c);
+    fq_add(h, b, a);
+    fq_mul(r.X, e, f);
+    fq_mul(r.Y, g, h);
+    fq_mul(r.Z, f, g);
+    if (WANT_T) fq_mul(r.T, e, h);
+}
+// extended + affine Niels (Z2 = 1): 7M (6M without T)
+template <bool WANT_T>
+JJS_HD void ext_add_niels(ext& r, const ext& p, const niels& q) {
+    fq a, b, c, d, e, f, g, h, t;
+    fq_sub(t, p.Y, p.X);
+    fq_mul(a, t, q.ymx);
+    fq_add(t, p.Y, p.X);
+    fq_mul(b, t, q.ypx);
+    fq_mul(c, p.T, q.t2d);
+    fq_dbl(d, p.Z);
+    fq_sub(e, b, a);
+    fq_sub(f, d, c);
+    fq_add(g, d, c);
+    fq_add(h, b, a);
+    fq_mul(r.X, e, f);
+    fq_mul(r.Y, g, h);
+    fq_mul(r.Z, f, g);
+    if (WANT_T) fq_mul(r.T, e, h);
+}
+JJS_HD void ext_to_pniels(pniels& n, const ext& p) {
+    fq d2;
+    fq_load_const(d2, JJS_C(EDWARDS_2D));
+    fq_add(n.ypx, p.Y, p.X);
+    fq_sub(n.ymx, p.Y, p.X);
+    fq_dbl(n.z2, p.Z);
+    fq_mul(n.t2d, p.T, d2);
+}
+JJS_HD void pniels_identity(pniels& n) {
+    fq_one(n.ypx);
+    fq_one(n.ymx);
+    fq_one(n.z2);
+    fq_dbl(n.z2, n.z2);
+    fq_zero(n.t2d);
+}
+// conditional negation: -(x, y) = (-x, y) swaps ypx/ymx and negates t2d
+JJS_HD void pniels_cneg(pniels& n, bool neg) {
+    fq nt;
+    fq_neg(nt, n.t2d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t a = n.ypx.l[i], b = n.ymx.l[i];
+        n.ypx.l[i] = neg ? b : a;
+        n.ymx.l[i] = neg ? a : b;
+        n.t2d.l[i] = neg ? nt.l[i] : n.t2d.l[i];
+    }
+}
+JJS_HD bool ext_is_identity(const ext& p) { return fq_is_zero(p.X) && fq_eq(p.Y, p.Z); }
+// projective point == affine point (u, v):  X == u Z and Y == v Z   (JubJubExtended::eq with Z2 = 1)
+JJS_HD bool ext_eq_affine(const ext& p, const fq& u, const fq& v) {
+    fq a, b;
+    fq_mul(a, u, p.Z);
+    fq_mul(b, v, p.Z);
+    return fq_eq(a, p.X) && fq_eq(b, p.Y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fixed-exponent powers, inversion, square root of a ratio (q - 1 = 2^32 t)
+// ---------------------------------------------------------------------------------------------
+
+// a^((t-1)/2) with the generated sliding-window schedule (odd powers a, a^3, ..., a^15)
+JJS_HD void fq_pow_tm1d2(fq& r, const fq& a) {
+    fq odd[8], a2;
+    odd[0] = a;
+    fq_sqr(a2, a);
+#pragma unroll 1
+    for (int i = 1; i < 8; i++) fq_mul(odd[i], odd[i - 1], a2);
+    fq acc = odd[JJS_C(SQRT_SCHED)[0][1]];
+#pragma unroll 1
+    for (int s = 1; s < JJS_SQRT_SCHED_LEN; s++) {
+        int nsq = JJS_C(SQRT_SCHED)[s][0], idx = JJS_C(SQRT_SCHED)[s][1];
+#pragma unroll 1
+        for (int k = 0; k < nsq; k++) fq_sqr(acc, acc);
+        if (idx != 0xff) fq_mul(acc, acc, odd[idx]);
+    }
+    r = acc;
+}
+// a^(q-2) (Fermat inversion; inv(0) = 0).  Only used off the hot path (table construction, aggregate keys).
+JJS_HD void fq_inv(fq& r, const fq& a) {
+    fq acc;
+    fq_one(acc);
+#pragma unroll 1
+    for (int i = 254; i >= 0; i--) {
+        fq_sqr(acc, acc);
+        if ((JJS_C(Q_MINUS_2)[i >> 5] >> (i & 31)) & 1) fq_mul(acc, acc, a);
+    }
+    r = acc;
+}
+
+JJS_HD uint32_t dlog8(const Tables& T, const fq& x) {  // x in mu_256 = <g^(2^24)>: its discrete log
+    uint32_t h = (x.l[0] * JJS_DLOG_HASH_MULT) >> (32 - JJS_DLOG_HASH_BITS);
+    return T.dlog_hash[h];
+}
+JJS_HD void root_table_load(fq& r, const Tables& T, int table, uint32_t j) { r = T.root_tables[table * 256 + j]; }
+
+// r = sqrt(num / den) if it exists (either root); returns false for a non-residue.  den != 0.
+// With a = num den, w = a^((t-1)/2), b = a w^2 = a^t lies in the 2^32-torsion <g>; writing b = g^k,
+// num / den is a square iff k is even and then sqrt(num/den) = num * w * g^(-k/2).  k is recovered 8 bits
+// at a time from b^(2^24), b^(2^16), b^(2^8), b and tables of g^(-j 2^i) (24 squarings + 6 products).
+JJS_HD bool fq_sqrt_ratio(fq& r, const fq& num, const fq& den, const Tables& T) {
+    fq a, w, b, p1, p2, p3, x, t;
+    fq_mul(a, num, den);
+    if (fq_is_zero(a)) {
+        fq_zero(r);
+        return true;
+    }
+    fq_pow_tm1d2(w, a);
+    fq_sqr(b, w);
+    fq_mul(b, b, a);
+    p1 = b;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) fq_sqr(p1, p1);
+    p2 = p1;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) fq_sqr(p2, p2);
+    p3 = p2;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) fq_sqr(p3, p3);
+    uint32_t k0 = dlog8(T, p3);
+    root_table_load(t, T, 2, k0);      // g^(-k0 2^16)
+    fq_mul(x, p2, t);
+    uint32_t k1 = dlog8(T, x);
+    root_table_load(t, T, 1, k0);      // g^(-k0 2^8)
+    fq_mul(x, p1, t);
+    root_table_load(t, T, 2, k1);      // g^(-k1 2^16)
+    fq_mul(x, x, t);
+    uint32_t k2 = dlog8(T, x);
+    root_table_load(t, T, 0, k0);      // g^(-k0)
+    fq_mul(x, b, t);
+    root_table_load(t, T, 1, k1);      // g^(-k1 2^8)
+    fq_mul(x, x, t);
+    root_table_load(t, T, 2, k2);      // g^(-k2 2^16)
+    fq_mul(x, x, t);
+    uint32_t k3 = dlog8(T, x);
+    if (k0 & 1) return false;
+    // num * w * g^(-k/2),  k/2 = k0/2 + 2^7 k1 + 2^15 k2 + 2^23 k3
+    fq_mul(x, num, w);
+    root_table_load(t, T, 0, k0 >> 1);
+    fq_mul(x, x, t);
+    root_table_load(t, T, 3, k1);
+    fq_mul(x, x, t);
+    root_table_load(t, T, 4, k2);
+    fq_mul(x, x, t);
+    root_table_load(t, T, 5, k3);
+    fq_mul(r, x, t);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wire decoding
+// ---------------------------------------------------------------------------------------------
+JJS_HD void load_le32(uint32_t* w, const uint8_t* p) {  // 32 bytes, 4-byte aligned -> 8 little-endian words
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = q[i];
+}
+JJS_HD void store_le32(uint8_t* p, const uint32_t* w) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = w[i];
+}
+// BlsScalar::from_bytes: canonical little-endian, reject >= q.  Output in Montgomery form.
+JJS_HD bool fq_from_wire(fq& r, const uint32_t* w) {
+    fq raw;
+#pragma unroll
+    for (int i = 0; i < 8; i++) raw.l[i] = w[i];
+    if (ge_q(raw.l)) return false;
+    fq_to_mont(r, raw);
+    return true;
+}
+// JubJubScalar::from_bytes: canonical little-endian, reject >= r (reference src/signatures.rs:113)
+JJS_HD bool fr_wire_is_canonical(const uint32_t* w) {
+    uint32_t ord[8], s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ord[i] = JJS_C(R_ORDER)[i];
+    return sub8(s, w, ord) != 0;  // borrow <=> w < r
+}
+// JubJubAffine::from_bytes: v little-endian with the parity of u in bit 255.
+// Rejects v >= q, u^2 a non-residue, and u == 0 with the sign bit set.  No subgroup check here.
+JJS_HD bool point_from_wire(fq& u, fq& v, const uint32_t* w_in, const Tables& T) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = w_in[i];
+    uint32_t sign = w[7] >> 31;
+    w[7] &= 0x7fffffffu;
+    if (!fq_from_wire(v, w)) return false;
+    fq v2, num, den, one, d;
+    fq_one(one);
+    fq_load_const(d, JJS_C(EDWARDS_D));
+    fq_sqr(v2, v);
+    fq_sub(num, v2, one);
+    fq_mul(den, v2, d);
+    fq_add(den, den, one);
+    if (!fq_sqrt_ratio(u, num, den, T)) return false;
+    fq canon;
+    fq_from_mont(canon, u);
+    bool flip = (canon.l[0] & 1u) != sign;
+    fq nu;
+    fq_neg(nu, u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) u.l[i] = flip ? nu.l[i] : u.l[i];
+    if (fq_is_zero(u) && sign) return false;
+    return true;
+}
+// JubJubAffine::to_bytes of an affine point given in Montgomery form
+JJS_HD void point_to_wire(uint32_t* w, const fq& u, const fq& v) {
+    fq cu, cv;
+    fq_from_mont(cu, u);
+    fq_from_mont(cv, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = cv.l[i];
+    w[7] |= (cu.l[0] & 1u) << 31;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar recoding and multiplication
+// ---------------------------------------------------------------------------------------------
+
+// signed radix-16 digits d_i in [-8, 8), i = 0..63, of a 256-bit little-endian scalar < 2^253
+JJS_HD void recode_signed16(int8_t* digits, const uint32_t* k) {
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        int d = (int)((k[i >> 3] >> ((i & 7) * 4)) & 15u) + (int)carry;
+        carry = d >= 8;
+        digits[i] = (int8_t)(d - (carry << 4));
+    }
+}
+
+// Per-thread table of 0..8 times a variable base in projective Niels form.  `tab` points at this
+// thread's first element; consecutive fq of one entry are `stride` elements apart (device: the batch
+// size, so a warp's accesses to one coordinate of one entry are contiguous; host: 1).
+JJS_HD void pniels_store(fq* tab, size_t stride, int entry, const pniels& n) {
+    fq* p = tab + (size_t)entry * 4 * stride;
+    p[0] = n.ypx;
+    p[stride] = n.ymx;
+    p[2 * stride] = n.z2;
+    p[3 * stride] = n.t2d;
+}
+JJS_HD void pniels_load(pniels& n, const fq* tab, size_t stride, int entry) {
+    const fq* p = tab + (size_t)entry * 4 * stride;
+    n.ypx = p[0];
+    n.ymx = p[stride];
+    n.z2 = p[2 * stride];
+    n.t2d = p[3 * stride];
+}
+JJS_HD void varbase_table_build(fq* tab, size_t stride, const fq& u, const fq& v) {
+    ext p, acc;
+    pniels n1, n;
+    ext_from_affine(p, u, v);
+    pniels_identity(n);
+    pniels_store(tab, stride, 0, n);
+    ext_to_pniels(n1, p);
+    pniels_store(tab, stride, 1, n1);
+    acc = p;
+#pragma unroll 1
+    for (int k = 2; k <= 8; k++) {
+        ext nx;
+        ext_add_pniels<true>(nx, acc, n1);
+        acc = nx;
+        ext_to_pniels(n, acc);
+        pniels_store(tab, stride, k, n);
+    }
+}
+// acc = 16 * acc + digit * P, digit in [-8, 8], P's multiples in `tab`
+template <bool WANT_T>
+JJS_HD void varbase_window(ext& acc, const fq* tab, size_t stride, int digit) {
+    ext t;
+    ext_dbl<false>(t, acc);
+    ext_dbl<false>(acc, t);
+    ext_dbl<false>(t, acc);
+    ext_dbl<true>(acc, t);
+    pniels n;
+    int mag = digit < 0 ? -digit : digit;
+    pniels_load(n, tab, stride, mag);
+    pniels_cneg(n, digit < 0);
+    ext_add_pniels<WANT_T>(t, acc, n);
+    acc = t;
+}
+// r = k * P for a table built by varbase_table_build; digits from recode_signed16 (64 digits).
+// r.T is only defined when WANT_T.
+template <bool WANT_T, typename DIGITS>
+JJS_HD void varbase_mul(ext& r, const fq* tab, size_t stride, const DIGITS& digits) {
+    ext acc;
+    {
+        pniels n;
+        int d = digits[63];
+        int mag = d < 0 ? -d : d;
+        pniels_load(n, tab, stride, mag);
+        pniels_cneg(n, d < 0);
+        ext id;
+        ext_identity(id);
+        ext_add_pniels<false>(acc, id, n);
+    }
+#pragma unroll 1
+    for (int i = 62; i >= 1; i--) varbase_window<false>(acc, tab, stride, digits[i]);
+    varbase_window<WANT_T>(acc, tab, stride, digits[0]);
+    r = acc;
+}
+
+// r = k * B for a fixed base with precomputed window tables: sum over windows of table[w][k_w] (mixed additions)
+JJS_HD void fixedbase_mul(ext& r, const niels* table, const uint32_t* k) {
+    ext acc;
+    ext_identity(acc);
+#pragma unroll 1
+    for (int w = 0; w < FB_WINDOWS; w++) {
+        int bit = w * FB_W;
+        uint32_t lo = k[bit >> 5] >> (bit & 31);
+        if ((bit & 31) + FB_W > 32 && (bit >> 5) + 1 < 8) lo |= k[(bit >> 5) + 1] << (32 - (bit & 31));
+        uint32_t idx = lo & (FB_ENTRIES - 1);
+        niels n = table[(size_t)w * FB_ENTRIES + idx];
+        ext t;
+        ext_add_niels<true>(t, acc, n);
+        acc = t;
+    }
+    r = acc;
+}
+
+// One entry of a fixed-base window table: j * 2^(FB_W w) * B as affine Niels (table construction only).
+JJS_HD void fb_table_entry(niels& out, const fq& bu, const fq& bv, int w, int j) {
+    ext base, acc, t;
+    pniels nb;
+    ext_from_affine(base, bu, bv);
+#pragma unroll 1
+    for (int i = 0; i < w * FB_W; i++) {
+        ext_dbl<true>(t, base);
+        base = t;
+    }
+    ext_to_pniels(nb, base);
+    ext_identity(acc);
+#pragma unroll 1
+    for (int b = FB_W - 1; b >= 0; b--) {
+        ext_dbl<true>(t, acc);
+        acc = t;
+        if ((j >> b) & 1) {
+            ext_add_pniels<true>(t, acc, nb);
+            acc = t;
+        }
+    }
+    fq zi, u, v, d2;
+    fq_inv(zi, acc.Z);
+    fq_mul(u, acc.X, zi);
+    fq_mul(v, acc.Y, zi);
+    fq_load_const(d2, JJS_C(EDWARDS_2D));
+    fq_add(out.ypx, v, u);
+    fq_sub(out.ymx, v, u);
+    fq_mul(out.t2d, u, v);
+    fq_mul(out.t2d, out.t2d, d2);
+}
+
+// [r] P == identity for a point given in affine coordinates (is_torsion_free)
+JJS_HD bool point_is_torsion_free(fq* tab, size_t stride, const fq& u, const fq& v) {
+    varbase_table_build(tab, stride, u, v);
+    ext m;
+    varbase_mul<false>(m, tab, stride, JJS_C(R_ORDER_DIGITS));
+    return ext_is_identity(m);
+}
+
+}  // namespace jjs

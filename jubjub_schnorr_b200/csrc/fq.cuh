@@ -1,0 +1,509 @@
+// BLS12-381 scalar field Fq (dusk-bls12_381 BlsScalar) on 8 x 32-bit Montgomery limbs for sm_100a.
+//
+// Every multi-limb carry chain is ONE inline-PTX block of mad.lo.cc / madc.hi.cc pairs, which ptxas
+// fuses into IMAD.WIDE.U32(.X) with predicate carries (one integer-pipe issue per 32x32->64 product).
+// Each block has a plain C++ twin under !__CUDA_ARCH__ so tests/hostsim can run the very same
+// algorithms (reduction schedule, curve formulas, Poseidon rewrite) on the CPU.  That twin is test
+// scaffolding: the shipped library never executes it.
+//
+// Replaces, for the verify direction, the Fq arithmetic the reference reaches through
+// dusk_bls12_381::BlsScalar (call sites: reference src/signatures.rs:127-139, src/keys/public.rs:128).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define JJS_HD __host__ __device__ __forceinline__
+#define JJS_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define JJS_HD inline
+#define JJS_HD_NOINLINE
+#endif
+
+#if !defined(__CUDACC__)
+struct uint4 {  // host twin of the CUDA vector type (tests/hostsim only)
+    uint32_t x, y, z, w;
+};
+#endif
+
+namespace jjs {
+
+// q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, little-endian 32-bit limbs.
+// -q^-1 mod 2^32 = 0xffffffff, so the Montgomery quotient digit is just the negated low limb.
+#define JJS_Q_LIMBS {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u}
+
+struct fq {
+    uint32_t l[8];
+};
+
+JJS_HD uint32_t q_limb(int i) {
+    constexpr uint32_t Q[8] = JJS_Q_LIMBS;
+    return Q[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// carry-chain building blocks (device: one asm block each; host: exact C++ twin)
+// ---------------------------------------------------------------------------------------------
+
+// acc[0..2N) += a[k] * b with product k at limb pair (2k, 2k+1); acc[2N] += carry out.  N in 1..4.
+template <int N>
+JJS_HD void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    if (N == 1) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, %2, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
+            : "r"(a[0]), "r"(b));
+    } else if (N == 2) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+            : "r"(a[0]), "r"(a[1]), "r"(b));
+    } else if (N == 3) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, %6, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b));
+    } else {
+        asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+              "+r"(acc[7]), "+r"(acc[8])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b));
+    }
+#else
+    uint64_t c = 0;
+    for (int k = 0; k < N; k++) {
+        uint64_t p = (uint64_t)a[k] * b;
+        uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + c;
+        acc[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+        acc[2 * k + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    acc[2 * N] += (uint32_t)c;
+#endif
+}
+
+// t[0..15] += a_i^2 at limb pair (2i, 2i+1), one carry chain over all 16 limbs (no carry out by construction).
+JJS_HD void mad_diag8(uint32_t* t, const uint32_t* a) {
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]),
+          "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+    uint64_t c = 0;
+    for (int k = 0; k < 8; k++) {
+        uint64_t p = (uint64_t)a[k] * a[k];
+        uint64_t lo = (uint64_t)t[2 * k] + (uint32_t)p + c;
+        t[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)t[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+        t[2 * k + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+#endif
+}
+
+// r[0..7] = x[0..7] + y[0..7] + cin (cin in {0,1}); returns carry out in {0,1}.
+JJS_HD uint32_t add8(uint32_t* r, const uint32_t* x, const uint32_t* y, uint32_t cin = 0) {
+    uint32_t cout;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"  // CF = cin
+        "addc.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(cout)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y[0]), "r"(y[1]),
+          "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]), "r"(cin));
+#else
+    uint64_t c = cin;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)x[i] + y[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    cout = (uint32_t)c;
+#endif
+    return cout;
+}
+
+// r = x - y over 8 limbs; returns 0xffffffff if the subtraction borrowed, else 0.
+JJS_HD uint32_t sub8(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+    uint32_t borrow;
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(borrow)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y[0]), "r"(y[1]),
+          "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]));
+#else
+    int64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (int64_t)x[i] - (int64_t)y[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    borrow = (uint32_t)c;
+#endif
+    return borrow;
+}
+
+// r = x - q; returns 0xffffffff if x < q (borrow), else 0.  q limbs are immediates.
+JJS_HD uint32_t sub_q(uint32_t* r, const uint32_t* x) {
+    uint32_t borrow;
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u32 %0, %9, 0x00000001;\n\t"
+        "subc.cc.u32 %1, %10, 0xffffffff;\n\t"
+        "subc.cc.u32 %2, %11, 0xfffe5bfe;\n\t"
+        "subc.cc.u32 %3, %12, 0x53bda402;\n\t"
+        "subc.cc.u32 %4, %13, 0x09a1d805;\n\t"
+        "subc.cc.u32 %5, %14, 0x3339d808;\n\t"
+        "subc.cc.u32 %6, %15, 0x299d7d48;\n\t"
+        "subc.cc.u32 %7, %16, 0x73eda753;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(borrow)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+#else
+    int64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (int64_t)x[i] - (int64_t)q_limb(i);
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    borrow = (uint32_t)c;
+#endif
+    return borrow;
+}
+
+// r = x + (q & mask) over 8 limbs (mask is 0 or 0xffffffff); carry out dropped.
+JJS_HD void add_q_masked(uint32_t* r, const uint32_t* x, uint32_t mask) {
+    constexpr uint32_t Q[8] = JJS_Q_LIMBS;
+    uint32_t y[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) y[i] = Q[i] & mask;
+    add8(r, x, y);
+}
+
+// One Montgomery reduction step on the (ev, od) split representation  V = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1)).
+// Precondition: ev[0] == 0 (its low limb was cancelled by the previous step; for the first step the
+// caller presents T shifted up by one limb).  The step shifts V right by 32 bits, picks the quotient
+// digit m = -(low limb), adds m*q and appends `inject` as the new top limb:
+//     e0     = od[0] + ev[1]                       (new limb 0, carry continues into the odd chain)
+//     m      = -e0
+//     n[0..8]= ev[2..8],inject  + m*(q1,q3,q5,q7)  (new odd accumulator, limbs 1..9)
+//     od[1..8]+= m*(q0,q2,q4,q6) with e0 + m*q0 == 0 (mod 2^32)   (new even accumulator is (0, od[1..8]))
+JJS_HD void redc_step(const uint32_t* ev, uint32_t* od, uint32_t* n, uint32_t inject) {
+#if defined(__CUDA_ARCH__)
+    uint32_t e0, m;
+    asm("add.cc.u32 %0, %11, %12;\n\t"
+        "sub.u32 %1, 0, %0;\n\t"
+        "madc.lo.cc.u32 %2, %1, 0xffffffff, %13;\n\t"
+        "madc.hi.cc.u32 %3, %1, 0xffffffff, %14;\n\t"
+        "madc.lo.cc.u32 %4, %1, 0x53bda402, %15;\n\t"
+        "madc.hi.cc.u32 %5, %1, 0x53bda402, %16;\n\t"
+        "madc.lo.cc.u32 %6, %1, 0x3339d808, %17;\n\t"
+        "madc.hi.cc.u32 %7, %1, 0x3339d808, %18;\n\t"
+        "madc.lo.cc.u32 %8, %1, 0x73eda753, %19;\n\t"
+        "madc.hi.cc.u32 %9, %1, 0x73eda753, %20;\n\t"
+        "addc.u32 %10, 0, 0;"
+        : "=&r"(e0), "=&r"(m), "=&r"(n[0]), "=&r"(n[1]), "=&r"(n[2]), "=&r"(n[3]), "=&r"(n[4]), "=&r"(n[5]), "=&r"(n[6]),
+          "=&r"(n[7]), "=&r"(n[8])
+        : "r"(od[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]),
+          "r"(inject));
+    asm("mad.lo.cc.u32 %0, %9, 0x00000001, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, 0x00000001, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, 0xfffe5bfe, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, 0xfffe5bfe, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, 0x09a1d805, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, 0x09a1d805, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, 0x299d7d48, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, 0x299d7d48, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(e0), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8])
+        : "r"(m));
+    od[0] = e0;  // == 0
+#else
+    constexpr uint32_t Q[8] = JJS_Q_LIMBS;
+    uint64_t s = (uint64_t)od[0] + ev[1];
+    uint32_t e0 = (uint32_t)s;
+    uint64_t c = s >> 32;
+    uint32_t m = 0u - e0;
+    const uint32_t addend[8] = {ev[2], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8], inject};
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)m * Q[2 * k + 1];
+        uint64_t lo = (uint64_t)addend[2 * k] + (uint32_t)p + c;
+        n[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)addend[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+        n[2 * k + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    n[8] = (uint32_t)c;
+    c = 0;
+    uint32_t* acc[8] = {&e0, &od[1], &od[2], &od[3], &od[4], &od[5], &od[6], &od[7]};
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)m * Q[2 * k];
+        uint64_t lo = (uint64_t)*acc[2 * k] + (uint32_t)p + c;
+        *acc[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)*acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+        *acc[2 * k + 1] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    od[8] += (uint32_t)c;
+    od[0] = e0;
+#endif
+}
+
+JJS_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi) {  // (hi:lo << 1) >> 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, 1);
+#else
+    return (hi << 1) | (lo >> 31);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// wide products and Montgomery reduction
+// ---------------------------------------------------------------------------------------------
+
+// t[0..15] = a * b (schoolbook, 64 wide multiplies in 16 carry chains over an even and an odd accumulator)
+JJS_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+    uint32_t E[17], O[15];  // E[k]: limb k;  O[k]: limb k+1
+#pragma unroll
+    for (int i = 0; i < 17; i++) E[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 15; i++) O[i] = 0;
+    const uint32_t ae[4] = {a[0], a[2], a[4], a[6]}, ao[4] = {a[1], a[3], a[5], a[7]};
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        mad_row<4>(E + i, ae, b[i]);
+        mad_row<4>(O + i, ao, b[i]);
+        mad_row<4>(O + i, ae, b[i + 1]);
+        mad_row<4>(E + i + 2, ao, b[i + 1]);
+    }
+    // t = E + (O << 32)
+    t[0] = E[0];
+    uint32_t c = add8(t + 1, E + 1, O);
+    uint32_t x[8] = {E[9], E[10], E[11], E[12], E[13], E[14], E[15], 0};
+    uint32_t y[8] = {O[8], O[9], O[10], O[11], O[12], O[13], O[14], 0};
+    uint32_t hi[8];
+    add8(hi, x, y, c);
+#pragma unroll
+    for (int i = 0; i < 7; i++) t[9 + i] = hi[i];
+}
+
+// t[0..15] = a^2 (28 off-diagonal + 8 diagonal wide multiplies)
+JJS_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
+    uint32_t E[16], O[16];  // E[k]: limb k;  O[k]: limb k+1
+#pragma unroll
+    for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
+    // row i multiplies a[i] with a[j], j > i: j - i odd -> odd accumulator, j - i even -> even accumulator
+    { const uint32_t m[4] = {a[1], a[3], a[5], a[7]}; mad_row<4>(O + 0, m, a[0]); }    // limbs 1..8
+    { const uint32_t m[3] = {a[2], a[4], a[6]};       mad_row<3>(E + 2, m, a[0]); }    // limbs 2..7
+    { const uint32_t m[3] = {a[2], a[4], a[6]};       mad_row<3>(O + 2, m, a[1]); }    // limbs 3..8
+    { const uint32_t m[3] = {a[3], a[5], a[7]};       mad_row<3>(E + 4, m, a[1]); }    // limbs 4..9
+    { const uint32_t m[3] = {a[3], a[5], a[7]};       mad_row<3>(O + 4, m, a[2]); }    // limbs 5..10
+    { const uint32_t m[2] = {a[4], a[6]};             mad_row<2>(E + 6, m, a[2]); }    // limbs 6..9
+    { const uint32_t m[2] = {a[4], a[6]};             mad_row<2>(O + 6, m, a[3]); }    // limbs 7..10
+    { const uint32_t m[2] = {a[5], a[7]};             mad_row<2>(E + 8, m, a[3]); }    // limbs 8..11
+    { const uint32_t m[2] = {a[5], a[7]};             mad_row<2>(O + 8, m, a[4]); }    // limbs 9..12
+    { const uint32_t m[1] = {a[6]};                   mad_row<1>(E + 10, m, a[4]); }   // limbs 10..11
+    { const uint32_t m[1] = {a[6]};                   mad_row<1>(O + 10, m, a[5]); }   // limbs 11..12
+    { const uint32_t m[1] = {a[7]};                   mad_row<1>(E + 12, m, a[5]); }   // limbs 12..13
+    { const uint32_t m[1] = {a[7]};                   mad_row<1>(O + 12, m, a[6]); }   // limbs 13..14
+    // s = E + (O << 32): limbs 1..15
+    uint32_t s[16];
+    s[0] = 0;
+    uint32_t lo[8] = {0, E[2], E[3], E[4], E[5], E[6], E[7], E[8]};
+    uint32_t c = add8(s + 1, lo, O);
+    uint32_t x[8] = {E[9], E[10], E[11], E[12], E[13], E[14], 0, 0};
+    uint32_t y[8] = {O[8], O[9], O[10], O[11], O[12], O[13], O[14], 0};
+    uint32_t hi[8];
+    add8(hi, x, y, c);
+#pragma unroll
+    for (int i = 0; i < 7; i++) s[9 + i] = hi[i];
+    // t = 2 s + diagonal
+#pragma unroll
+    for (int i = 15; i >= 1; i--) t[i] = funnel_l1(s[i - 1], s[i]);
+    t[0] = 0;
+    mad_diag8(t, a);
+}
+
+// r = t / 2^256 mod q for a 16-limb t < q * 2^256 (so the result is < 2q before the final subtraction).
+JJS_HD void redc(uint32_t* r, const uint32_t* t) {
+    uint32_t ev[9], od[9], n[9];
+    ev[0] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ev[i + 1] = t[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) od[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        redc_step(ev, od, n, t[8 + i]);
+#pragma unroll
+        for (int k = 0; k < 9; k++) { ev[k] = od[k]; od[k] = n[k]; }
+    }
+    // value = (ev >> 32) + od, with ev[0] == 0
+    uint32_t v[8];
+    add8(v, ev + 1, od);
+    uint32_t s[8];
+    uint32_t borrow = sub_q(s, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? v[i] : s[i];
+}
+
+// r = v / 2^32 mod q for a 9-limb v < 2^32 * q (one Montgomery step; used after small-integer linear maps)
+JJS_HD void redc_one(uint32_t* r, const uint32_t* v) {
+    uint32_t ev[9], od[9], n[9];
+    ev[0] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ev[i + 1] = v[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) od[i] = 0;
+    redc_step(ev, od, n, v[8]);
+    uint32_t w[8], s[8];
+    add8(w, od + 1, n);
+    uint32_t borrow = sub_q(s, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? w[i] : s[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// field API (all values fully reduced, Montgomery form unless stated)
+// ---------------------------------------------------------------------------------------------
+JJS_HD void fq_mul_inl(fq& r, const fq& a, const fq& b) {
+    uint32_t t[16];
+    mul_wide(t, a.l, b.l);
+    redc(r.l, t);
+}
+JJS_HD void fq_sqr_inl(fq& r, const fq& a) {
+    uint32_t t[16];
+    sqr_wide(t, a.l);
+    redc(r.l, t);
+}
+// On the device the multiplier and squarer are real functions (operands travel in registers, no stack
+// frame): ~20 moves per call buy a >10x smaller instruction footprint, so the hot loops of the curve and
+// hash kernels stay resident in the SM instruction caches.  -DJJS_INLINE_FIELD inlines them instead.
+#if defined(__CUDA_ARCH__) && !defined(JJS_INLINE_FIELD)
+__device__ __noinline__ fq fq_mul_fn(fq a, fq b) {
+    fq r;
+    fq_mul_inl(r, a, b);
+    return r;
+}
+__device__ __noinline__ fq fq_sqr_fn(fq a) {
+    fq r;
+    fq_sqr_inl(r, a);
+    return r;
+}
+JJS_HD void fq_mul(fq& r, const fq& a, const fq& b) { r = fq_mul_fn(a, b); }
+JJS_HD void fq_sqr(fq& r, const fq& a) { r = fq_sqr_fn(a); }
+#else
+JJS_HD void fq_mul(fq& r, const fq& a, const fq& b) { fq_mul_inl(r, a, b); }
+JJS_HD void fq_sqr(fq& r, const fq& a) { fq_sqr_inl(r, a); }
+#endif
+JJS_HD void fq_add(fq& r, const fq& a, const fq& b) {
+    uint32_t v[8], s[8];
+    add8(v, a.l, b.l);  // < 2q < 2^256
+    uint32_t borrow = sub_q(s, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = borrow ? v[i] : s[i];
+}
+JJS_HD void fq_sub(fq& r, const fq& a, const fq& b) {
+    uint32_t v[8];
+    uint32_t borrow = sub8(v, a.l, b.l);
+    add_q_masked(r.l, v, borrow);
+}
+JJS_HD void fq_dbl(fq& r, const fq& a) { fq_add(r, a, a); }
+JJS_HD void fq_neg(fq& r, const fq& a) {
+    fq z;
+#pragma unroll
+    for (int i = 0; i < 8; i++) z.l[i] = 0;
+    fq_sub(r, z, a);
+}
+JJS_HD bool fq_is_zero(const fq& a) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x |= a.l[i];
+    return x == 0;
+}
+JJS_HD bool fq_eq(const fq& a, const fq& b) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x |= a.l[i] ^ b.l[i];
+    return x == 0;
+}
+JJS_HD void fq_zero(fq& r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = 0;
+}
+// Montgomery R = 2^256 mod q
+JJS_HD void fq_one(fq& r) {
+    constexpr uint32_t R1[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = R1[i];
+}
+// canonical integer (< q) -> Montgomery: multiply by R^2
+JJS_HD void fq_to_mont(fq& r, const fq& a) {
+    constexpr uint32_t R2[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+    fq r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.l[i] = R2[i];
+    fq_mul(r, a, r2);
+}
+// Montgomery -> canonical integer
+JJS_HD void fq_from_mont(fq& r, const fq& a) {
+    uint32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { t[i] = a.l[i]; t[8 + i] = 0; }
+    redc(r.l, t);
+}
+// x >= q ?  (x any 256-bit value)
+JJS_HD bool ge_q(const uint32_t* x) {
+    uint32_t s[8];
+    return sub_q(s, x) == 0;
+}
+
+}  // namespace jjs

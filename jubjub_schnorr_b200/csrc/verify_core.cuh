@@ -1,0 +1,168 @@
+// Per-item stages of batch Schnorr verification (single / double / var-generator), shared by the CUDA
+// kernels (kernels.cu) and by the CPU twin used in tests/hostsim.
+//
+// Semantics follow the reference exactly (status codes in include/jjschnorr_b200.h):
+//   from_bytes of every field                    -> 3 (BytesError)      reference src/signatures.rs:112-117, src/keys/public.rs:87-94
+//   is_valid() of key and signature points       -> 2 (InvalidPoint)    reference src/keys/public.rs:119-121, 159-164
+//   c = challenge_hash(..)                                              reference src/signatures.rs:122-141 (+ double.rs:151-177, var_gen.rs:121-142)
+//   u*G + c*PK == R (both equations for double)  -> 1 (InvalidSignature) reference src/keys/public.rs:128-132
+#pragma once
+#include "curve.cuh"
+#include "poseidon.cuh"
+
+namespace jjs {
+
+enum Variant : int { VAR_SINGLE = 0, VAR_DOUBLE = 1, VAR_VARGEN = 2 };
+
+// point flags
+constexpr uint8_t PF_DECODED = 1;       // from_bytes succeeded
+constexpr uint8_t PF_IDENTITY = 2;      // is_identity()
+constexpr uint8_t PF_TORSION_FREE = 4;  // is_torsion_free()
+// item flags
+constexpr uint8_t IF_SCALARS_OK = 1;    // u < r and m < q
+constexpr uint8_t IF_EQ0_OK = 2;
+constexpr uint8_t IF_EQ1_OK = 4;
+
+struct WireField {
+    const uint8_t* base;
+    uint32_t stride;
+};
+
+JJS_HD void wire_load(uint32_t* w, const WireField& f, size_t i) {
+    const uint4* p = reinterpret_cast<const uint4*>(f.base + i * f.stride);
+    uint4 a = p[0], b = p[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+
+// number of point fields per item and their order in the decoded-point arrays
+//   single: 0 = PK, 1 = R            double: 0 = PK, 1 = PK', 2 = R, 3 = R'        var-gen: 0 = PK, 1 = generator, 2 = R
+JJS_HD int variant_slots(int variant) { return variant == VAR_SINGLE ? 2 : (variant == VAR_DOUBLE ? 4 : 3); }
+
+// ---- stage 1: decode one point ---------------------------------------------------------------
+JJS_HD void stage_decode(const WireField& f, size_t item, fq* out_u, fq* out_v, uint8_t* out_flags, size_t slot_index,
+                         const Tables& T) {
+    uint32_t w[8];
+    wire_load(w, f, item);
+    fq u, v;
+    bool ok = point_from_wire(u, v, w, T);
+    uint8_t fl = 0;
+    if (ok) {
+        fq one;
+        fq_one(one);
+        fl = PF_DECODED | ((fq_is_zero(u) && fq_eq(v, one)) ? PF_IDENTITY : 0);
+        out_u[slot_index] = u;
+        out_v[slot_index] = v;
+    }
+    out_flags[slot_index] = fl;
+}
+
+// ---- stage 2: challenge hash -------------------------------------------------------------------
+// pts_u / pts_v are [slots][n]; writes the challenge as 8 little-endian words and the scalar-range flag.
+JJS_HD void stage_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n, size_t item,
+                            const WireField& msg, const WireField& usc, uint32_t* c_out, uint8_t* item_flags) {
+    uint32_t w[8];
+    fq m;
+    wire_load(w, msg, item);
+    bool ok = fq_from_wire(m, w);
+    wire_load(w, usc, item);
+    ok = ok && fr_wire_is_canonical(w);
+    const int slots = variant_slots(variant);
+    bool decoded = true;
+    for (int s = 0; s < slots; s++) decoded = decoded && (pflags[s * n + item] & PF_DECODED);
+    item_flags[item] = ok ? IF_SCALARS_OK : 0;
+    uint32_t c[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = 0;
+    if (ok && decoded) {
+        Sponge sp;
+        if (variant == VAR_SINGLE) {  // [R.u, R.v, pk.u, pk.v, m]
+            sponge_start(sp, 5);
+            sponge_absorb(sp, pts_u[1 * n + item]);
+            sponge_absorb(sp, pts_v[1 * n + item]);
+            sponge_absorb(sp, pts_u[0 * n + item]);
+            sponge_absorb(sp, pts_v[0 * n + item]);
+            sponge_absorb(sp, m);
+        } else if (variant == VAR_DOUBLE) {  // [JJSCHDBL, R, R', pk, pk', m]
+            sponge_start(sp, 10);
+            fq tag;
+            fq_load_const(tag, JJS_C(DOUBLE_DOMAIN));
+            sponge_absorb(sp, tag);
+            sponge_absorb(sp, pts_u[2 * n + item]);
+            sponge_absorb(sp, pts_v[2 * n + item]);
+            sponge_absorb(sp, pts_u[3 * n + item]);
+            sponge_absorb(sp, pts_v[3 * n + item]);
+            sponge_absorb(sp, pts_u[0 * n + item]);
+            sponge_absorb(sp, pts_v[0 * n + item]);
+            sponge_absorb(sp, pts_u[1 * n + item]);
+            sponge_absorb(sp, pts_v[1 * n + item]);
+            sponge_absorb(sp, m);
+        } else {  // [R, pk, generator, m]
+            sponge_start(sp, 7);
+            sponge_absorb(sp, pts_u[2 * n + item]);
+            sponge_absorb(sp, pts_v[2 * n + item]);
+            sponge_absorb(sp, pts_u[0 * n + item]);
+            sponge_absorb(sp, pts_v[0 * n + item]);
+            sponge_absorb(sp, pts_u[1 * n + item]);
+            sponge_absorb(sp, pts_v[1 * n + item]);
+            sponge_absorb(sp, m);
+        }
+        sponge_squeeze_truncated(c, sp);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) c_out[item * 8 + i] = c[i];
+}
+
+// ---- stage 3: subgroup membership of one decoded point ------------------------------------------
+JJS_HD void stage_subgroup(const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t slot_index, fq* tab, size_t stride) {
+    uint8_t fl = pflags[slot_index];
+    if (!(fl & PF_DECODED)) return;
+    if (point_is_torsion_free(tab, stride, pts_u[slot_index], pts_v[slot_index])) pflags[slot_index] = fl | PF_TORSION_FREE;
+}
+
+// ---- stage 4: one verification equation  u*B + c*PK == R ------------------------------------------
+// base_slot < 0: fixed base table `fb`; otherwise the decoded point in that slot is the base (var-gen).
+JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t item, int pk_slot, int r_slot, int base_slot,
+                           const niels* fb, const WireField& usc, const uint32_t* c_words, fq* tab, size_t stride) {
+    uint32_t u[8], c[8];
+    wire_load(u, usc, item);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = c_words[item * 8 + i];
+    int8_t digits[64];
+    ext acc, ub;
+    // c * PK
+    varbase_table_build(tab, stride, pts_u[pk_slot * n + item], pts_v[pk_slot * n + item]);
+    recode_signed16(digits, c);
+    varbase_mul<true>(acc, tab, stride, digits);
+    // u * B
+    if (base_slot < 0) {
+        fixedbase_mul(ub, fb, u);
+    } else {
+        varbase_table_build(tab, stride, pts_u[base_slot * n + item], pts_v[base_slot * n + item]);
+        recode_signed16(digits, u);
+        varbase_mul<true>(ub, tab, stride, digits);
+    }
+    pniels nb;
+    ext_to_pniels(nb, ub);
+    ext sum;
+    ext_add_pniels<false>(sum, acc, nb);
+    return ext_eq_affine(sum, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
+}
+
+// ---- stage 5: combine flags into the reference's result -----------------------------------------
+JJS_HD uint8_t stage_status(int variant, const uint8_t* pflags, uint8_t item_flags, size_t n, size_t item) {
+    const int slots = variant_slots(variant);
+    bool decoded = (item_flags & IF_SCALARS_OK) != 0;
+    bool valid = true;
+    for (int s = 0; s < slots; s++) {
+        uint8_t f = pflags[s * n + item];
+        decoded = decoded && (f & PF_DECODED);
+        valid = valid && (f & PF_TORSION_FREE) && !(f & PF_IDENTITY);
+    }
+    if (!decoded) return 3;
+    if (!valid) return 2;
+    bool eq = (item_flags & IF_EQ0_OK) && (variant != VAR_DOUBLE || (item_flags & IF_EQ1_OK));
+    return eq ? 0 : 1;
+}
+
+}  // namespace jjs

@@ -1,0 +1,169 @@
+// Host build of the device headers (their C++ twins of the PTX blocks) so the algorithms can be checked
+// on a CPU-only machine.  Test scaffolding: never linked into libjjschnorr_b200.so.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../jubjub_schnorr_b200/csrc/verify_core.cuh"
+namespace tables {
+#include "../../jubjub_schnorr_b200/csrc/jjs_constants_tables.h"
+}
+
+using namespace jjs;
+
+static std::vector<niels> g_fb_g, g_fb_gn;
+static Tables g_tables;
+static bool g_ready = false;
+
+static void build_fb(std::vector<niels>& out, const uint32_t uv[2][8]) {
+    fq u, v;
+    memcpy(u.l, uv[0], 32);
+    memcpy(v.l, uv[1], 32);
+    out.resize((size_t)FB_WINDOWS * FB_ENTRIES);
+    // incremental construction (fb_table_entry itself is exercised by hs_fb_entry)
+    ext base;
+    ext_from_affine(base, u, v);
+    for (int w = 0; w < FB_WINDOWS; w++) {
+        pniels nb;
+        ext_to_pniels(nb, base);
+        ext acc;
+        ext_identity(acc);
+        for (int j = 0; j < FB_ENTRIES; j++) {
+            fq zi, au, av, d2;
+            fq_inv(zi, acc.Z);
+            fq_mul(au, acc.X, zi);
+            fq_mul(av, acc.Y, zi);
+            fq_load_const(d2, JJS_C(EDWARDS_2D));
+            niels& e = out[(size_t)w * FB_ENTRIES + j];
+            fq_add(e.ypx, av, au);
+            fq_sub(e.ymx, av, au);
+            fq_mul(e.t2d, au, av);
+            fq_mul(e.t2d, e.t2d, d2);
+            ext t;
+            ext_add_pniels<true>(t, acc, nb);
+            acc = t;
+        }
+        base = acc;  // 2^FB_W * previous base
+    }
+}
+
+static void ensure_ready() {
+    if (g_ready) return;
+    g_tables.root_tables = reinterpret_cast<const fq*>(tables::ROOT_TABLES);
+    g_tables.dlog_hash = tables::DLOG_HASH;
+    build_fb(g_fb_g, hconsts::GEN_UV);
+    build_fb(g_fb_gn, hconsts::GEN_NUMS_UV);
+    g_tables.fb_g = g_fb_g.data();
+    g_tables.fb_gn = g_fb_gn.data();
+    g_ready = true;
+}
+
+extern "C" {
+void hs_mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* t16) { mul_wide(t16, a, b); }
+void hs_sqr_wide(const uint32_t* a, uint32_t* t16) { sqr_wide(t16, a); }
+void hs_redc(const uint32_t* t16, uint32_t* r8) { redc(r8, t16); }
+void hs_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { fq x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fq_mul(z, x, y); memcpy(r, z.l, 32); }
+void hs_fq_sqr(const uint32_t* a, uint32_t* r) { fq x, z; memcpy(x.l, a, 32); fq_sqr(z, x); memcpy(r, z.l, 32); }
+void hs_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { fq x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fq_add(z, x, y); memcpy(r, z.l, 32); }
+void hs_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { fq x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fq_sub(z, x, y); memcpy(r, z.l, 32); }
+void hs_fq_to_mont(const uint32_t* a, uint32_t* r) { fq x, z; memcpy(x.l, a, 32); fq_to_mont(z, x); memcpy(r, z.l, 32); }
+void hs_fq_from_mont(const uint32_t* a, uint32_t* r) { fq x, z; memcpy(x.l, a, 32); fq_from_mont(z, x); memcpy(r, z.l, 32); }
+void hs_fq_inv(const uint32_t* a, uint32_t* r) { fq x, z; memcpy(x.l, a, 32); fq_inv(z, x); memcpy(r, z.l, 32); }
+// sqrt(num/den), Montgomery in/out; returns 0 for non-residue
+int hs_sqrt_ratio(const uint32_t* num, const uint32_t* den, uint32_t* r) {
+    ensure_ready();
+    fq x, y, z;
+    memcpy(x.l, num, 32); memcpy(y.l, den, 32);
+    bool ok = fq_sqrt_ratio(z, x, y, g_tables);
+    memcpy(r, z.l, 32);
+    return ok;
+}
+// canonical 5-lane state in/out
+void hs_hades_permute(uint32_t* state40) {
+    fq s[5];
+    for (int i = 0; i < 5; i++) { fq c; memcpy(c.l, state40 + 8 * i, 32); fq_to_mont(s[i], c); }
+    hades_permute(s);
+    for (int i = 0; i < 5; i++) { fq c; fq_from_mont(c, s[i]); memcpy(state40 + 8 * i, c.l, 32); }
+}
+int hs_point_decode(const uint8_t* in32, uint32_t* uv16) {  // canonical (u, v) out
+    ensure_ready();
+    uint32_t w[8];
+    memcpy(w, in32, 32);
+    fq u, v, cu, cv;
+    if (!point_from_wire(u, v, w, g_tables)) return 0;
+    fq_from_mont(cu, u); fq_from_mont(cv, v);
+    memcpy(uv16, cu.l, 32); memcpy(uv16 + 8, cv.l, 32);
+    return 1;
+}
+void hs_fb_entry(int which, int w, int j, uint32_t* out24, uint32_t* ref24) {  // fb_table_entry vs incremental table
+    ensure_ready();
+    fq u, v;
+    const uint32_t (*uv)[8] = which ? hconsts::GEN_NUMS_UV : hconsts::GEN_UV;
+    memcpy(u.l, uv[0], 32); memcpy(v.l, uv[1], 32);
+    niels e;
+    fb_table_entry(e, u, v, w, j);
+    memcpy(out24, &e, 96);
+    memcpy(ref24, &(which ? g_fb_gn : g_fb_g)[(size_t)w * FB_ENTRIES + j], 96);
+}
+// k * P for a compressed point, k a 256-bit LE scalar < 2^253 ; returns compressed result (uses varbase path)
+int hs_varbase_mul(const uint8_t* p32, const uint8_t* k32, uint8_t* out32, int fixed_base /*0 none, 1 G, 2 G'*/) {
+    ensure_ready();
+    uint32_t w[8], k[8];
+    memcpy(k, k32, 32);
+    ext r;
+    if (fixed_base) {
+        fixedbase_mul(r, fixed_base == 1 ? g_tables.fb_g : g_tables.fb_gn, k);
+    } else {
+        memcpy(w, p32, 32);
+        fq u, v;
+        if (!point_from_wire(u, v, w, g_tables)) return 0;
+        std::vector<fq> tab(36);
+        varbase_table_build(tab.data(), 1, u, v);
+        int8_t digits[64];
+        recode_signed16(digits, k);
+        varbase_mul<true>(r, tab.data(), 1, digits);
+    }
+    fq zi, au, av;
+    fq_inv(zi, r.Z);
+    fq_mul(au, r.X, zi);
+    fq_mul(av, r.Y, zi);
+    uint32_t o[8];
+    point_to_wire(o, au, av);
+    memcpy(out32, o, 32);
+    return 1;
+}
+// Whole pipeline through the same stage functions the kernels call.
+void hs_verify(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status, uint8_t* c_out) {
+    ensure_ready();
+    const int slots = variant_slots(variant);
+    uint32_t pk_stride = variant == VAR_SINGLE ? 32 : 64, sig_stride = variant == VAR_DOUBLE ? 96 : 64;
+    WireField f[4], fmsg{msg, 32}, fu{sig, sig_stride};
+    if (variant == VAR_SINGLE) { f[0] = {pk, 32}; f[1] = {sig + 32, 64}; }
+    else if (variant == VAR_DOUBLE) { f[0] = {pk, 64}; f[1] = {pk + 32, 64}; f[2] = {sig + 32, 96}; f[3] = {sig + 64, 96}; }
+    else { f[0] = {pk, 64}; f[1] = {pk + 32, 64}; f[2] = {sig + 32, 64}; }
+    (void)pk_stride;
+    std::vector<fq> pu(slots * n), pv(slots * n), tab(36);
+    std::vector<uint8_t> pf(slots * n), itf(n);
+    std::vector<uint32_t> cw(8 * n);
+    for (int s = 0; s < slots; s++)
+        for (size_t i = 0; i < n; i++) stage_decode(f[s], i, pu.data(), pv.data(), pf.data(), s * n + i, g_tables);
+    for (size_t i = 0; i < n; i++) stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
+    for (size_t k = 0; k < slots * n; k++) stage_subgroup(pu.data(), pv.data(), pf.data(), k, tab.data(), 1);
+    for (size_t i = 0; i < n; i++) {
+        bool all = (itf[i] & IF_SCALARS_OK);
+        for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);
+        if (all) {
+            if (variant == VAR_SINGLE) {
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
+            } else if (variant == VAR_DOUBLE) {
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, -1, g_tables.fb_g, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
+                if (stage_equation(pu.data(), pv.data(), n, i, 1, 3, -1, g_tables.fb_gn, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ1_OK;
+            } else {
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, 1, nullptr, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
+            }
+        }
+        status[i] = stage_status(variant, pf.data(), itf[i], n, i);
+        if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
+    }
+}
+}
