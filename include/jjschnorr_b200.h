@@ -1,0 +1,104 @@
+/*
+ * jjschnorr_b200 -- C ABI of the B200-native batch verifier for dusk-network/jubjub-schnorr signatures.
+ *
+ * This is the drop-in boundary for the reference's verify path: every entry point consumes the
+ * reference's own wire encodings and reproduces the result of the reference call it replaces, bit for
+ * bit.  A Rust caller binds these through `extern "C"`; nothing here exposes C++
+ * or torch types, nothing throws, and there is no CPU fallback: if no usable CUDA device is present the
+ * calls return JJS_ERR_CUDA.
+ *
+ * Wire encodings (all little-endian, exactly `to_bytes()` of the reference types):
+ *   PublicKey        32 B  compressed point                       reference src/keys/public.rs:80-94
+ *   Signature        64 B  u (32) || R (32)                       reference src/signatures.rs:101-118
+ *   PublicKeyDouble  64 B  pk || pk'                              reference src/keys/public/double.rs:169-186
+ *   SignatureDouble  96 B  u || R || R'                           reference src/signatures/double.rs:122-147
+ *   PublicKeyVarGen  64 B  pk || generator                        reference src/keys/public/var_gen.rs:54-79
+ *   SignatureVarGen  64 B  u || R                                 reference src/signatures/var_gen.rs:95-112
+ *   message          32 B  BlsScalar::to_bytes()
+ * Arrays are contiguous, item i at base + i * size.
+ *
+ * Per-item result (status byte), mirroring Result<(), Error> of the reference (src/error.rs:13-26):
+ *   JJS_OK                 Ok(())
+ *   JJS_INVALID_SIGNATURE  Err(Error::InvalidSignature)   the verification equation does not hold
+ *   JJS_INVALID_POINT      Err(Error::InvalidPoint)       a key / signature point fails is_valid()
+ *   JJS_BYTES_ERROR        Err(Error::BytesError(_))      some field fails from_bytes()
+ * with the reference's precedence: decoding, then point validity, then the equation.
+ * The optional challenge output receives c = challenge_hash(..) as JubJubScalar::to_bytes() for items
+ * whose status is JJS_OK or JJS_INVALID_SIGNATURE and 32 zero bytes otherwise (the reference does not
+ * compute a challenge for those).
+ */
+#ifndef JJSCHNORR_B200_H
+#define JJSCHNORR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JJS_OK 0
+#define JJS_INVALID_SIGNATURE 1
+#define JJS_INVALID_POINT 2
+#define JJS_BYTES_ERROR 3
+
+/* call return codes */
+#define JJS_SUCCESS 0
+#define JJS_ERR_ARGUMENT (-1)
+#define JJS_ERR_CUDA (-2)
+#define JJS_ERR_NOMEM (-3)
+
+typedef struct jjs_ctx jjs_ctx;
+
+/* Create a context over the given CUDA device ordinals (n_devices >= 1; devices == NULL means device 0
+ * .. n_devices-1).  Builds the per-device constant tables and allocates no batch memory yet. */
+int jjs_init(const int* devices, int n_devices, jjs_ctx** out);
+void jjs_destroy(jjs_ctx* ctx);
+/* Human-readable description of the last failure on this context ("" if none). */
+const char* jjs_last_error(const jjs_ctx* ctx);
+int jjs_device_count(const jjs_ctx* ctx);
+
+/* ---- host-buffer entry points: shard the batch contiguously over the context's devices, copy in,
+ *      verify, copy the status bytes (and challenges) back.  All pointers are host memory. -------------- */
+
+/* PublicKey::verify for n (key, signature, message) triples.  reference src/keys/public.rs:114-135 */
+int jjs_verify_single(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n,
+                      uint8_t* status, uint8_t* c32_or_null);
+/* PublicKeyDouble::verify.  reference src/keys/public/double.rs:86-117 */
+int jjs_verify_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n,
+                      uint8_t* status, uint8_t* c32_or_null);
+/* PublicKeyVarGen::verify.  reference src/keys/public/var_gen.rs:107-133 */
+int jjs_verify_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig64, const uint8_t* msg32, size_t n,
+                      uint8_t* status, uint8_t* c32_or_null);
+/* multisig::aggregate_pk(&pks[offsets[i]..offsets[i+1]]).verify(sig_i, msg_i).
+ * reference src/multisig.rs:154-156, 393-429 then src/keys/public.rs:114-135.
+ * offsets has n + 1 entries; aggpk32_or_null receives PublicKey::to_bytes() of each aggregate key. */
+int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* offsets, const uint8_t* sig64,
+                         const uint8_t* msg32, size_t n, uint8_t* status, uint8_t* c32_or_null,
+                         uint8_t* aggpk32_or_null);
+
+/* ---- device-buffer entry points: inputs and outputs already live on device `device_index` of the context
+ *      (an index into the list given to jjs_init); the work is enqueued on `cuda_stream` (a cudaStream_t,
+ *      NULL = the context's own stream) and is complete when that stream is.  No host copies. ---------- */
+int jjs_verify_single_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk32, const uint8_t* d_sig64,
+                             const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
+                             void* cuda_stream);
+int jjs_verify_double_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk64, const uint8_t* d_sig96,
+                             const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
+                             void* cuda_stream);
+int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk64, const uint8_t* d_sig64,
+                             const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
+                             void* cuda_stream);
+
+/* Challenge hash only (hash parity hook): c = challenge_hash(..) for already-valid encodings, no curve
+ * check.  variant: 0 single, 1 double, 2 var-generator.  Host buffers. */
+int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32,
+                       size_t n, uint8_t* c32);
+
+/* Kernels launched by this context since creation (for the bench's gpu_launches accounting). */
+uint64_t jjs_launch_count(const jjs_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JJSCHNORR_B200_H */

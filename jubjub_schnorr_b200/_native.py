@@ -1,0 +1,61 @@
+"""ctypes loader for libjjschnorr_b200.so (the CUDA library; C ABI in include/jjschnorr_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or no sm_100a device is usable,
+every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libjjschnorr_b200.so")
+
+EXPORTS = [
+    "jjs_init", "jjs_destroy", "jjs_last_error", "jjs_device_count", "jjs_launch_count",
+    "jjs_verify_single", "jjs_verify_double", "jjs_verify_vargen", "jjs_verify_aggregate",
+    "jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device",
+    "jjs_challenge_only",
+]
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  jubjub_schnorr_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.jjs_init.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.jjs_init.restype = C.c_int
+    L.jjs_destroy.argtypes = [vp]
+    L.jjs_destroy.restype = None
+    L.jjs_last_error.argtypes = [vp]
+    L.jjs_last_error.restype = C.c_char_p
+    L.jjs_device_count.argtypes = [vp]
+    L.jjs_device_count.restype = C.c_int
+    L.jjs_launch_count.argtypes = [vp]
+    L.jjs_launch_count.restype = C.c_uint64
+    for name in ("jjs_verify_single", "jjs_verify_double", "jjs_verify_vargen"):
+        f = getattr(L, name)
+        f.argtypes = [vp, vp, vp, vp, sz, vp, vp]
+        f.restype = C.c_int
+    L.jjs_verify_aggregate.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
+    L.jjs_verify_aggregate.restype = C.c_int
+    for name in ("jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device"):
+        f = getattr(L, name)
+        f.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, vp]
+        f.restype = C.c_int
+    L.jjs_challenge_only.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp]
+    L.jjs_challenge_only.restype = C.c_int
+    _lib = L
+    return L

@@ -1,0 +1,126 @@
+"""Batch entry points over numpy / raw device buffers (thin wrappers of the C ABI, include/jjschnorr_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+
+STATUS_OK, STATUS_INVALID_SIGNATURE, STATUS_INVALID_POINT, STATUS_BYTES_ERROR = 0, 1, 2, 3
+SINGLE, DOUBLE, VARGEN = 0, 1, 2
+PK_SIZE = {SINGLE: 32, DOUBLE: 64, VARGEN: 64}
+SIG_SIZE = {SINGLE: 64, DOUBLE: 96, VARGEN: 64}
+
+
+class JjsError(RuntimeError):
+    pass
+
+
+def _u8(a, width, name):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.size % width:
+        raise ValueError(f"{name}: byte length {a.size} is not a multiple of {width}")
+    return a.reshape(-1, width)
+
+
+class BatchVerifier:
+    """Owns a jjs_ctx over one or more CUDA devices.  One host thread at a time."""
+
+    def __init__(self, devices=None):
+        self._lib = _native.lib()
+        self._ctx = C.c_void_p()
+        if devices is None:
+            devices = [0]
+        arr = (C.c_int * len(devices))(*devices)
+        rc = self._lib.jjs_init(arr, len(devices), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.jjs_last_error(self._ctx).decode() if self._ctx else "allocation failed"
+            if self._ctx:
+                self._lib.jjs_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise JjsError(f"jjs_init failed ({rc}): {msg}")
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.jjs_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise JjsError(f"{what} failed ({rc}): {self._lib.jjs_last_error(self._ctx).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.jjs_launch_count(self._ctx))
+
+    # ---- host buffers ---------------------------------------------------------------------------
+    def _verify_host(self, variant, fn, name, pk, sig, msg, want_challenge):
+        pk, sig, msg = _u8(pk, PK_SIZE[variant], "pk"), _u8(sig, SIG_SIZE[variant], "sig"), _u8(msg, 32, "msg")
+        n = msg.shape[0]
+        if pk.shape[0] != n or sig.shape[0] != n:
+            raise ValueError("pk, sig and msg must describe the same number of items")
+        status = np.empty(n, dtype=np.uint8)
+        c = np.empty((n, 32), dtype=np.uint8) if want_challenge else None
+        self._check(fn(self._ctx, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, n, status.ctypes.data,
+                       c.ctypes.data if want_challenge else None), name)
+        return (status, c) if want_challenge else status
+
+    def verify_single(self, pk32, sig64, msg32, want_challenge=False):
+        return self._verify_host(SINGLE, self._lib.jjs_verify_single, "jjs_verify_single", pk32, sig64, msg32, want_challenge)
+
+    def verify_double(self, pk64, sig96, msg32, want_challenge=False):
+        return self._verify_host(DOUBLE, self._lib.jjs_verify_double, "jjs_verify_double", pk64, sig96, msg32, want_challenge)
+
+    def verify_vargen(self, pk64, sig64, msg32, want_challenge=False):
+        return self._verify_host(VARGEN, self._lib.jjs_verify_vargen, "jjs_verify_vargen", pk64, sig64, msg32, want_challenge)
+
+    def verify_aggregate(self, pks32, offsets, sig64, msg32, want_challenge=False, want_aggregate_key=False):
+        pks, sig, msg = _u8(pks32, 32, "pks"), _u8(sig64, 64, "sig"), _u8(msg32, 32, "msg")
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = msg.shape[0]
+        if offsets.shape[0] != n + 1 or sig.shape[0] != n or int(offsets[-1]) != pks.shape[0] or int(offsets[0]) != 0:
+            raise ValueError("offsets must have n + 1 entries covering pks32 exactly")
+        status = np.empty(n, dtype=np.uint8)
+        c = np.empty((n, 32), dtype=np.uint8) if want_challenge else None
+        agg = np.empty((n, 32), dtype=np.uint8) if want_aggregate_key else None
+        self._check(self._lib.jjs_verify_aggregate(self._ctx, pks.ctypes.data, offsets.ctypes.data, sig.ctypes.data, msg.ctypes.data, n,
+                                                   status.ctypes.data, c.ctypes.data if want_challenge else None,
+                                                   agg.ctypes.data if want_aggregate_key else None), "jjs_verify_aggregate")
+        out = [status]
+        if want_challenge:
+            out.append(c)
+        if want_aggregate_key:
+            out.append(agg)
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def challenge_only(self, variant, pk, sig, msg32):
+        pk, sig, msg = _u8(pk, PK_SIZE[variant], "pk"), _u8(sig, SIG_SIZE[variant], "sig"), _u8(msg32, 32, "msg")
+        n = msg.shape[0]
+        c = np.empty((n, 32), dtype=np.uint8)
+        self._check(self._lib.jjs_challenge_only(self._ctx, variant, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, n, c.ctypes.data),
+                    "jjs_challenge_only")
+        return c
+
+    # ---- raw host / device pointers (pinned torch tensors, device tensors: pass .data_ptr()) ----------
+    def verify_host_ptr(self, variant, pk_ptr, sig_ptr, msg_ptr, n, status_ptr, c_ptr=None):
+        fn = {SINGLE: self._lib.jjs_verify_single, DOUBLE: self._lib.jjs_verify_double, VARGEN: self._lib.jjs_verify_vargen}[variant]
+        self._check(fn(self._ctx, pk_ptr, sig_ptr, msg_ptr, n, status_ptr, c_ptr), "jjs_verify (host pointers)")
+
+    def verify_device(self, variant, d_pk, d_sig, d_msg, n, d_status, d_c=None, stream=None, device_index=0):
+        fn = {SINGLE: self._lib.jjs_verify_single_device, DOUBLE: self._lib.jjs_verify_double_device,
+              VARGEN: self._lib.jjs_verify_vargen_device}[variant]
+        self._check(fn(self._ctx, device_index, d_pk, d_sig, d_msg, n, d_status, d_c, stream), "jjs_verify (device pointers)")

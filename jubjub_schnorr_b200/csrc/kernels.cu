@@ -1,0 +1,407 @@
+// CUDA kernels (sm_100a) and the C ABI of libjjschnorr_b200.so.  See include/jjschnorr_b200.h for the
+// contract and verify_core.cuh for the per-item stages.  One thread owns one point (decode, subgroup
+// check), one item (challenge sponge, final status) or one verification equation (Straus-style
+// u*B + c*PK); intermediates travel between the stages as SoA arrays of 32-byte field elements in HBM,
+// so every warp access is a run of 128-bit vector loads.  There is deliberately no CPU path.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/jjschnorr_b200.h"
+#include "verify_core.cuh"
+
+namespace tables {
+#include "jjs_constants_tables.h"
+}
+
+using namespace jjs;
+
+namespace {
+
+constexpr int BLOCK = 128;
+constexpr size_t CHUNK_ITEMS = size_t(1) << 20;   // items per pipeline pass
+constexpr size_t TAB_THREADS = size_t(1) << 21;   // threads served by the per-thread table scratch (1152 B each)
+
+struct Fields {
+    WireField f[4];
+};
+
+__global__ void __launch_bounds__(BLOCK) k_decode(Fields fields, int slots, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags, Tables T) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)slots * n) return;
+    int slot = (int)(t / n);
+    size_t item = t - (size_t)slot * n;
+    stage_decode(fields.f[slot], item, pts_u, pts_v, pflags, t, T);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n,
+                                                     WireField msg, WireField usc, uint32_t* cwords, uint8_t* iflags) {
+    size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n) return;
+    stage_challenge(variant, pts_u, pts_v, pflags, n, item, msg, usc, cwords, iflags);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_subgroup(const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t first, size_t count,
+                                                    fq* tab, size_t stride) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    stage_subgroup(pts_u, pts_v, pflags, first + t, tab + t, stride);
+}
+
+// thread t < neq * n : equation t / n of item t % n
+__global__ void __launch_bounds__(BLOCK) k_equation(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags,
+                                                    const uint8_t* iflags, size_t n, size_t first, size_t count, WireField usc,
+                                                    const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    size_t g = first + t;
+    int eq = (int)(g / n);
+    size_t item = g - (size_t)eq * n;
+    const int slots = variant_slots(variant);
+    bool ready = (iflags[item] & IF_SCALARS_OK) != 0;
+    for (int s = 0; s < slots; s++) ready = ready && (pflags[s * n + item] & PF_DECODED);
+    bool ok = false;
+    if (ready) {
+        if (variant == VAR_SINGLE) ok = stage_equation(pts_u, pts_v, n, item, 0, 1, -1, T.fb_g, usc, cwords, tab + t, stride);
+        else if (variant == VAR_DOUBLE)
+            ok = eq == 0 ? stage_equation(pts_u, pts_v, n, item, 0, 2, -1, T.fb_g, usc, cwords, tab + t, stride)
+                         : stage_equation(pts_u, pts_v, n, item, 1, 3, -1, T.fb_gn, usc, cwords, tab + t, stride);
+        else ok = stage_equation(pts_u, pts_v, n, item, 0, 2, 1, nullptr, usc, cwords, tab + t, stride);
+    }
+    eqflags[g] = ok ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_finalize(int variant, const uint8_t* pflags, const uint8_t* iflags, const uint8_t* eqflags,
+                                                    const uint32_t* cwords, size_t n, uint8_t* status, uint8_t* c_out) {
+    size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n) return;
+    uint8_t fl = iflags[item];
+    if (eqflags[item]) fl |= IF_EQ0_OK;
+    if (variant == VAR_DOUBLE && eqflags[n + item]) fl |= IF_EQ1_OK;
+    uint8_t st = stage_status(variant, pflags, fl, n, item);
+    status[item] = st;
+    if (c_out) {
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (st <= 1) {
+            const uint4* p = reinterpret_cast<const uint4*>(cwords + item * 8);
+            a = p[0];
+            b = p[1];
+        }
+        uint4* o = reinterpret_cast<uint4*>(c_out + item * 32);
+        o[0] = a;
+        o[1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_fb_table(niels* out, int which) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= FB_WINDOWS * FB_ENTRIES) return;
+    fq u, v;
+    fq_load_const(u, which ? JJS_C(GEN_NUMS_UV)[0] : JJS_C(GEN_UV)[0]);
+    fq_load_const(v, which ? JJS_C(GEN_NUMS_UV)[1] : JJS_C(GEN_UV)[1]);
+    niels e;
+    fb_table_entry(e, u, v, t / FB_ENTRIES, t % FB_ENTRIES);
+    out[t] = e;
+}
+
+struct DeviceState {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    fq* root_tables = nullptr;
+    uint8_t* dlog_hash = nullptr;
+    niels* fb_g = nullptr;
+    niels* fb_gn = nullptr;
+    // pipeline scratch, sized for CHUNK_ITEMS items of the widest variant (4 points, 2 equations)
+    fq *pts_u = nullptr, *pts_v = nullptr, *tab = nullptr;
+    uint8_t *pflags = nullptr, *iflags = nullptr, *eqflags = nullptr;
+    uint32_t* cwords = nullptr;
+    // staging for the host-buffer entry points
+    uint8_t *s_pk = nullptr, *s_sig = nullptr, *s_msg = nullptr, *s_status = nullptr, *s_c = nullptr;
+    size_t stage_items = 0;
+    Tables tables() const { return Tables{root_tables, dlog_hash, fb_g, fb_gn}; }
+};
+
+}  // namespace
+
+struct jjs_ctx {
+    std::vector<DeviceState> dev;
+    char err[512];
+    uint64_t launches;
+};
+
+namespace {
+
+int fail(jjs_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define JJS_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? JJS_ERR_NOMEM : JJS_ERR_CUDA, \
+                                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline unsigned blocks_for(size_t threads) { return (unsigned)((threads + BLOCK - 1) / BLOCK); }
+
+int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
+    if (d.pts_u) return JJS_SUCCESS;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    JJS_CUDA(ctx, cudaMalloc(&d.pts_u, sizeof(fq) * 4 * CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.pts_v, sizeof(fq) * 4 * CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.pflags, 4 * CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.iflags, CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.eqflags, 2 * CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.cwords, 32 * CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * 36 * TAB_THREADS));
+    return JJS_SUCCESS;
+}
+
+int ensure_staging(jjs_ctx* ctx, DeviceState& d, size_t items) {
+    if (items <= d.stage_items) return JJS_SUCCESS;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
+    d.s_pk = d.s_sig = d.s_msg = d.s_status = d.s_c = nullptr;
+    d.stage_items = 0;
+    JJS_CUDA(ctx, cudaMalloc(&d.s_pk, 64 * items));
+    JJS_CUDA(ctx, cudaMalloc(&d.s_sig, 96 * items));
+    JJS_CUDA(ctx, cudaMalloc(&d.s_msg, 32 * items));
+    JJS_CUDA(ctx, cudaMalloc(&d.s_status, items));
+    JJS_CUDA(ctx, cudaMalloc(&d.s_c, 32 * items));
+    d.stage_items = items;
+    return JJS_SUCCESS;
+}
+
+void variant_fields(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, Fields& pts, WireField& fmsg, WireField& fu) {
+    fmsg = WireField{msg, 32};
+    if (variant == VAR_SINGLE) {
+        pts.f[0] = WireField{pk, 32};
+        pts.f[1] = WireField{sig + 32, 64};
+        pts.f[2] = pts.f[3] = WireField{nullptr, 0};
+        fu = WireField{sig, 64};
+    } else if (variant == VAR_DOUBLE) {
+        pts.f[0] = WireField{pk, 64};
+        pts.f[1] = WireField{pk + 32, 64};
+        pts.f[2] = WireField{sig + 32, 96};
+        pts.f[3] = WireField{sig + 64, 96};
+        fu = WireField{sig, 96};
+    } else {
+        pts.f[0] = WireField{pk, 64};
+        pts.f[1] = WireField{pk + 32, 64};
+        pts.f[2] = WireField{sig + 32, 64};
+        pts.f[3] = WireField{nullptr, 0};
+        fu = WireField{sig, 64};
+    }
+}
+inline size_t pk_size(int variant) { return variant == VAR_SINGLE ? 32 : 64; }
+inline size_t sig_size(int variant) { return variant == VAR_DOUBLE ? 96 : 64; }
+
+// Enqueue the whole pipeline for n items (device pointers) on `stream`.
+int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
+               uint8_t* status, uint8_t* c_out, cudaStream_t stream, bool challenge_only = false) {
+    int rc = ensure_scratch(ctx, d);
+    if (rc) return rc;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    const int slots = variant_slots(variant);
+    const int neq = variant == VAR_DOUBLE ? 2 : 1;
+    Tables T = d.tables();
+    for (size_t off = 0; off < n; off += CHUNK_ITEMS) {
+        size_t m = n - off < CHUNK_ITEMS ? n - off : CHUNK_ITEMS;
+        Fields pts;
+        WireField fmsg, fu;
+        variant_fields(variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, pts, fmsg, fu);
+        k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, m, d.pts_u, d.pts_v, d.pflags, T);
+        k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
+        ctx->launches += 2;
+        if (challenge_only) {
+            JJS_CUDA(ctx, cudaMemcpyAsync(c_out + off * 32, d.cwords, 32 * m, cudaMemcpyDeviceToDevice, stream));
+            continue;
+        }
+        for (size_t first = 0; first < slots * m; first += TAB_THREADS) {
+            size_t cnt = slots * m - first < TAB_THREADS ? slots * m - first : TAB_THREADS;
+            k_subgroup<<<blocks_for(cnt), BLOCK, 0, stream>>>(d.pts_u, d.pts_v, d.pflags, first, cnt, d.tab, TAB_THREADS);
+            ctx->launches++;
+        }
+        for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
+            size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
+            k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, d.iflags, m, first, cnt, fu, d.cwords,
+                                                             d.eqflags, d.tab, TAB_THREADS, T);
+            ctx->launches++;
+        }
+        k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, status + off,
+                                                       c_out ? c_out + off * 32 : nullptr);
+        ctx->launches++;
+    }
+    JJS_CUDA(ctx, cudaGetLastError());
+    return JJS_SUCCESS;
+}
+
+// Host-buffer path: contiguous shards over the context's devices, one stream each, joined before return.
+int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status,
+             uint8_t* c_out, bool challenge_only = false) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (n == 0) return JJS_SUCCESS;
+    if (!pk || !sig || !msg || (!status && !challenge_only) || (challenge_only && !c_out)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    const size_t g = ctx->dev.size();
+    const size_t per = (n + g - 1) / g;
+    const size_t pks = pk_size(variant), sgs = sig_size(variant);
+    for (size_t k = 0; k < g; k++) {
+        size_t lo = k * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        DeviceState& d = ctx->dev[k];
+        size_t m = hi - lo;
+        int rc = ensure_staging(ctx, d, m);
+        if (rc) return rc;
+        JJS_CUDA(ctx, cudaSetDevice(d.device));
+        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_pk, pk + lo * pks, m * pks, cudaMemcpyHostToDevice, d.stream));
+        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_sig, sig + lo * sgs, m * sgs, cudaMemcpyHostToDevice, d.stream));
+        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_msg, msg + lo * 32, m * 32, cudaMemcpyHostToDevice, d.stream));
+        rc = run_device(ctx, d, variant, d.s_pk, d.s_sig, d.s_msg, m, d.s_status, (c_out || challenge_only) ? d.s_c : nullptr, d.stream,
+                        challenge_only);
+        if (rc) return rc;
+        if (!challenge_only) JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, d.s_status, m, cudaMemcpyDeviceToHost, d.stream));
+        if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + lo * 32, d.s_c, m * 32, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (size_t k = 0; k < g; k++) {
+        JJS_CUDA(ctx, cudaSetDevice(ctx->dev[k].device));
+        JJS_CUDA(ctx, cudaStreamSynchronize(ctx->dev[k].stream));
+    }
+    return JJS_SUCCESS;
+}
+
+int init_device(jjs_ctx* ctx, DeviceState& d) {
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    cudaDeviceProp prop;
+    JJS_CUDA(ctx, cudaGetDeviceProperties(&prop, d.device));
+    if (prop.major != 10) return fail(ctx, JJS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d.device, prop.major, prop.minor);
+    JJS_CUDA(ctx, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    JJS_CUDA(ctx, cudaMalloc(&d.root_tables, sizeof(tables::ROOT_TABLES)));
+    JJS_CUDA(ctx, cudaMemcpy(d.root_tables, tables::ROOT_TABLES, sizeof(tables::ROOT_TABLES), cudaMemcpyHostToDevice));
+    JJS_CUDA(ctx, cudaMalloc(&d.dlog_hash, sizeof(tables::DLOG_HASH)));
+    JJS_CUDA(ctx, cudaMemcpy(d.dlog_hash, tables::DLOG_HASH, sizeof(tables::DLOG_HASH), cudaMemcpyHostToDevice));
+    const size_t fb_bytes = sizeof(niels) * FB_WINDOWS * FB_ENTRIES;
+    JJS_CUDA(ctx, cudaMalloc(&d.fb_g, fb_bytes));
+    JJS_CUDA(ctx, cudaMalloc(&d.fb_gn, fb_bytes));
+    k_fb_table<<<blocks_for(FB_WINDOWS * FB_ENTRIES), BLOCK, 0, d.stream>>>(d.fb_g, 0);
+    k_fb_table<<<blocks_for(FB_WINDOWS * FB_ENTRIES), BLOCK, 0, d.stream>>>(d.fb_gn, 1);
+    ctx->launches += 2;
+    JJS_CUDA(ctx, cudaGetLastError());
+    JJS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return JJS_SUCCESS;
+}
+
+void free_device(DeviceState& d) {
+    if (d.device < 0) return;
+    cudaSetDevice(d.device);
+    cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
+    cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords);
+    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
+    if (d.stream) cudaStreamDestroy(d.stream);
+}
+
+int device_entry(jjs_ctx* ctx, int variant, int device_index, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
+                 uint8_t* status, uint8_t* c_out, void* stream) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (device_index < 0 || (size_t)device_index >= ctx->dev.size()) return fail(ctx, JJS_ERR_ARGUMENT, "device_index out of range");
+    if (n == 0) return JJS_SUCCESS;
+    if (!pk || !sig || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    DeviceState& d = ctx->dev[device_index];
+    return run_device(ctx, d, variant, pk, sig, msg, n, status, c_out, stream ? (cudaStream_t)stream : d.stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+#define JJS_API __attribute__((visibility("default")))
+
+JJS_API int jjs_init(const int* devices, int n_devices, jjs_ctx** out) {
+    if (!out || n_devices < 1 || n_devices > 64) return JJS_ERR_ARGUMENT;
+    *out = nullptr;
+    jjs_ctx* ctx = new (std::nothrow) jjs_ctx();
+    if (!ctx) return JJS_ERR_NOMEM;
+    ctx->err[0] = 0;
+    ctx->launches = 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1) {
+        // no CPU fallback: the context is returned unusable only so the caller can read the reason
+        fail(ctx, JJS_ERR_CUDA, "no CUDA device available: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        *out = ctx;
+        return JJS_ERR_CUDA;
+    }
+    ctx->dev.resize(n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        ctx->dev[i].device = devices ? devices[i] : i;
+        if (ctx->dev[i].device < 0 || ctx->dev[i].device >= count) {
+            fail(ctx, JJS_ERR_ARGUMENT, "device ordinal %d not present (%d devices)", ctx->dev[i].device, count);
+            ctx->dev[i].device = -1;
+            *out = ctx;
+            return JJS_ERR_ARGUMENT;
+        }
+        int rc = init_device(ctx, ctx->dev[i]);
+        if (rc) {
+            *out = ctx;
+            return rc;
+        }
+    }
+    *out = ctx;
+    return JJS_SUCCESS;
+}
+
+JJS_API void jjs_destroy(jjs_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->dev) free_device(d);
+    delete ctx;
+}
+
+JJS_API const char* jjs_last_error(const jjs_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+JJS_API int jjs_device_count(const jjs_ctx* ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+JJS_API uint64_t jjs_launch_count(const jjs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+JJS_API int jjs_verify_single(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint8_t* status,
+                              uint8_t* c32_or_null) {
+    return run_host(ctx, VAR_SINGLE, pk32, sig64, msg32, n, status, c32_or_null);
+}
+JJS_API int jjs_verify_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n, uint8_t* status,
+                              uint8_t* c32_or_null) {
+    return run_host(ctx, VAR_DOUBLE, pk64, sig96, msg32, n, status, c32_or_null);
+}
+JJS_API int jjs_verify_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint8_t* status,
+                              uint8_t* c32_or_null) {
+    return run_host(ctx, VAR_VARGEN, pk64, sig64, msg32, n, status, c32_or_null);
+}
+JJS_API int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t*, const uint32_t*, const uint8_t*, const uint8_t*, size_t, uint8_t*, uint8_t*,
+                                 uint8_t*) {
+    return fail(ctx, JJS_ERR_ARGUMENT, "jjs_verify_aggregate: not implemented yet");
+}
+JJS_API int jjs_verify_single_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk32, const uint8_t* d_sig64, const uint8_t* d_msg32,
+                                     size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {
+    return device_entry(ctx, VAR_SINGLE, device_index, d_pk32, d_sig64, d_msg32, n, d_status, d_c32_or_null, cuda_stream);
+}
+JJS_API int jjs_verify_double_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk64, const uint8_t* d_sig96, const uint8_t* d_msg32,
+                                     size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {
+    return device_entry(ctx, VAR_DOUBLE, device_index, d_pk64, d_sig96, d_msg32, n, d_status, d_c32_or_null, cuda_stream);
+}
+JJS_API int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk64, const uint8_t* d_sig64, const uint8_t* d_msg32,
+                                     size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {
+    return device_entry(ctx, VAR_VARGEN, device_index, d_pk64, d_sig64, d_msg32, n, d_status, d_c32_or_null, cuda_stream);
+}
+JJS_API int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32, size_t n, uint8_t* c32) {
+    if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
+    return run_host(ctx, variant, pk, sig, msg32, n, nullptr, c32, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+"""GPU parity: the CUDA path (through the C ABI) against the pinned oracle, item by item."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import jjs_oracle as o
+from tests import adversarial as adv
+from tests.test_oracle_kat import legacy_double_fixture
+
+pytestmark = pytest.mark.gpu
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kat.json")))
+
+
+@pytest.fixture(scope="module")
+def bv():
+    from jubjub_schnorr_b200 import BatchVerifier
+    with BatchVerifier([0]) as v:
+        yield v
+
+
+def _a(b):
+    return np.frombuffer(bytes(b), dtype=np.uint8)
+
+
+def test_reference_kats_on_gpu(bv):
+    k, s = KAT["multisig_kat"], KAT["serde_kat"]
+    st, c = bv.verify_single(_a(bytes.fromhex(k["AGGREGATE_PUBLIC_KEY"])), _a(bytes.fromhex(k["SIGNATURE"])), _a(o.le32(31)), True)
+    assert st[0] == 0 and c.tobytes().hex() == k["CHALLENGE"]
+    m = bytes.fromhex("6dfe107145b1cba63d5f5ed0c410c09441fbc0d70c9bfea970949499aa128214")
+    st, c = bv.verify_single(_a(o.b58decode(s["serde_public_key"], 32)), _a(o.b58decode(s["serde_signature"], 64)), _a(m), True)
+    assert st[0] == 0 and c.tobytes().hex() == "7ad531e479fe4f1d2c1858c180e18f57e549d7eda93c85f46344f4716de67e02"
+    st, c = bv.verify_double(_a(o.b58decode(s["serde_public_key_double"], 64)), _a(o.b58decode(s["serde_signature_double"], 96)), _a(m), True)
+    assert st[0] == 0 and c.tobytes().hex() == "b706ff0423cbdff51e73ee23985e66a5f827343f03ecf4e9ecd7f32fc9791901"
+    rng = o.StdRng(s["_seed"]); rng.random_fr(); rng.random_fr()
+    mv = o.le32(rng.random_fq())
+    st, c = bv.verify_vargen(_a(o.b58decode(s["serde_public_key_var_gen"], 64)), _a(o.b58decode(s["serde_signature_var_gen"], 64)), _a(mv), True)
+    assert st[0] == 0 and c.tobytes().hex() == "648cf37f901b93870bec5cb3d7339934efd8307d7c667a3718cd14643a677603"
+    pkb, sig, mb = legacy_double_fixture()
+    assert bv.verify_double(_a(pkb), _a(sig), _a(mb))[0] == 1
+
+
+@pytest.mark.parametrize("kind,n", [("single", 4096), ("double", 2048), ("vargen", 2048)])
+def test_adversarial_batch_matches_oracle(bv, kind, n):
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    cver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    gver = {"single": bv.verify_single, "double": bv.verify_double, "vargen": bv.verify_vargen}[kind]
+    pk, sig, msg = gen(0xB200, n)
+    pk, sig, msg, expected, names = adv.make_adversarial(kind, pk, sig, msg, seed=11, frac=0.4)
+    st_o, c_o = cver(pk, sig, msg)
+    st_g, c_g = gver(pk, sig, msg, True)
+    bad = np.nonzero(st_g != st_o)[0]
+    assert bad.size == 0, [(int(i), names[i], int(st_g[i]), int(st_o[i])) for i in bad[:10]]
+    assert np.array_equal(st_o, expected)
+    assert np.array_equal(c_g, c_o)
+    assert set(st_g.tolist()) == {0, 1, 2, 3}
+
+
+def test_challenge_only_matches_oracle(bv):
+    pk, sig, msg = co.gen_single(3, 512)
+    _, c_o = co.verify_single(pk, sig, msg)
+    assert np.array_equal(bv.challenge_only(0, pk, sig, msg), c_o)
+
+
+def test_ragged_and_empty(bv):
+    for n in (0, 1, 31, 33, 129):
+        pk, sig, msg = co.gen_single(5, n)
+        st = bv.verify_single(pk, sig, msg)
+        assert st.shape == (n,) and (st == 0).all()
