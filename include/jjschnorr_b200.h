@@ -78,8 +78,9 @@ int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* off
                          uint8_t* aggpk32_or_null);
 
 /* ---- device-buffer entry points: inputs and outputs already live on device `device_index` of the context
- *      (an index into the list given to jjs_init); the work is enqueued on `cuda_stream` (a cudaStream_t,
- *      NULL = the context's own stream) and is complete when that stream is.  No host copies. ---------- */
+ *      (an index into the list given to jjs_init); the work is enqueued on `cuda_stream` (a cudaStream_t used
+ *      as is: NULL is the legacy default stream) and is complete when that stream is.  Calls on one context
+ *      share its scratch memory, so keep them on one stream or order them yourself.  No host copies. --- */
 int jjs_verify_single_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk32, const uint8_t* d_sig64,
                              const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
                              void* cuda_stream);
@@ -94,6 +95,26 @@ int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk
  * check.  variant: 0 single, 1 double, 2 var-generator.  Host buffers. */
 int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32,
                        size_t n, uint8_t* c32);
+
+/* Batch key derivation + signing on device 0 of the context (used to make large
+ * synthetic batches and by the tests).  For each item: pk = PublicKey::from(&sk) (reference
+ * src/keys/public.rs:54-60; PublicKeyDouble / PublicKeyVarGen likewise) and sig = sk.sign(rng, msg) with the
+ * reference's hedged nonce (src/keys/secret.rs:174-194, src/nonce.rs:32-86; sign_double: src/keys/secret/double.rs:57-85;
+ * var-gen: src/keys/secret/var_gen.rs), where rnd32 is the JubJubScalar the reference draws from its RNG
+ * and, for variant 2, the generator is gen_scalar * GENERATOR_EXTENDED as in SecretKeyVarGen::random.
+ * All scalars are canonical 32-byte little-endian (sk, rnd, gen_scalar < r; msg < q); an item with an
+ * out-of-range input yields all-zero outputs.  Host buffers.  NOT constant-time: test data only. */
+int jjs_sign_batch(jjs_ctx* ctx, int variant, const uint8_t* sk32, const uint8_t* rnd32,
+                   const uint8_t* gen_scalar32_or_null, const uint8_t* msg32, size_t n, uint8_t* pk_out,
+                   uint8_t* sig_out);
+
+/* Per-stage device timing (CUDA events on the launching stream around each pipeline stage):
+ * stage 0 point decode, 1 challenge hash, 2 subgroup checks, 3 verification equations, 4 status.
+ * jjs_profile_collect waits for the recorded events, adds their durations (ms) and occurrence counts per
+ * stage into the two JJS_N_STAGES-long arrays, and clears the records. */
+#define JJS_N_STAGES 5
+void jjs_profile_enable(jjs_ctx* ctx, int on);
+int jjs_profile_collect(jjs_ctx* ctx, double* stage_ms, uint64_t* stage_count);
 
 /* Kernels launched by this context since creation (for the bench's gpu_launches accounting). */
 uint64_t jjs_launch_count(const jjs_ctx* ctx);

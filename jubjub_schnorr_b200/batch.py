@@ -67,6 +67,18 @@ class BatchVerifier:
     def launch_count(self) -> int:
         return int(self._lib.jjs_launch_count(self._ctx))
 
+    STAGES = ("decode", "challenge", "subgroup", "equation", "status")
+
+    def profile(self, on: bool):
+        self._lib.jjs_profile_enable(self._ctx, int(on))
+
+    def profile_collect(self):
+        """{stage: (total_ms, launches)} since the last collect (waits for the recorded events)."""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_uint64 * 5)()
+        self._check(self._lib.jjs_profile_collect(self._ctx, ms, cnt), "jjs_profile_collect")
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.STAGES)}
+
     # ---- host buffers ---------------------------------------------------------------------------
     def _verify_host(self, variant, fn, name, pk, sig, msg, want_challenge):
         pk, sig, msg = _u8(pk, PK_SIZE[variant], "pk"), _u8(sig, SIG_SIZE[variant], "sig"), _u8(msg, 32, "msg")
@@ -114,6 +126,19 @@ class BatchVerifier:
         self._check(self._lib.jjs_challenge_only(self._ctx, variant, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, n, c.ctypes.data),
                     "jjs_challenge_only")
         return c
+
+    def sign_batch(self, variant, sk32, rnd32, msg32, gen_scalar32=None):
+        """(pk bytes, sig bytes) for n items; mirrors PublicKey::from(&sk) + sk.sign(rng, msg) of the reference."""
+        sk, rnd, msg = _u8(sk32, 32, "sk"), _u8(rnd32, 32, "rnd"), _u8(msg32, 32, "msg")
+        n = msg.shape[0]
+        gsc = _u8(gen_scalar32, 32, "gen_scalar") if gen_scalar32 is not None else None
+        if variant == VARGEN and gsc is None:
+            raise ValueError("var-generator signing needs gen_scalar32")
+        pk = np.empty((n, PK_SIZE[variant]), dtype=np.uint8)
+        sig = np.empty((n, SIG_SIZE[variant]), dtype=np.uint8)
+        self._check(self._lib.jjs_sign_batch(self._ctx, variant, sk.ctypes.data, rnd.ctypes.data, gsc.ctypes.data if gsc is not None else None,
+                                             msg.ctypes.data, n, pk.ctypes.data, sig.ctypes.data), "jjs_sign_batch")
+        return pk, sig
 
     # ---- raw host / device pointers (pinned torch tensors, device tensors: pass .data_ptr()) ----------
     def verify_host_ptr(self, variant, pk_ptr, sig_ptr, msg_ptr, n, status_ptr, c_ptr=None):

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/jjschnorr_b200.h"
+#include "sign_core.cuh"
 #include "verify_core.cuh"
 
 namespace tables {
@@ -108,6 +109,28 @@ __global__ void __launch_bounds__(BLOCK) k_fb_table(niels* out, int which) {
     out[t] = e;
 }
 
+// one thread signs one item; inputs are 32-byte little-endian scalars, outputs the reference's wire bytes.
+// The variant is a template parameter so that every array index below is static.
+template <int VARIANT>
+__global__ void __launch_bounds__(BLOCK) k_sign(const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, size_t n,
+                                                uint8_t* pk_out, uint8_t* sig_out, Tables T) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int PKW = VARIANT == VAR_SINGLE ? 8 : 16, SGW = VARIANT == VAR_DOUBLE ? 24 : 16;
+    uint32_t wsk[8], wrnd[8], wg[8], wm[8], pk[16], sig[24];
+    wire_load(wsk, WireField{sk, 32}, i);
+    wire_load(wrnd, WireField{rnd, 32}, i);
+    wire_load(wm, WireField{msg, 32}, i);
+    if (VARIANT == VAR_VARGEN) wire_load(wg, WireField{gsc, 32}, i);
+    bool ok = sign_item(VARIANT, wsk, wrnd, wg, wm, pk, sig, T);
+    uint4* po = reinterpret_cast<uint4*>(pk_out + i * PKW * 4);
+    uint4* so = reinterpret_cast<uint4*>(sig_out + i * SGW * 4);
+#pragma unroll
+    for (int k = 0; k < PKW / 4; k++) po[k] = ok ? make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < SGW / 4; k++) so[k] = ok ? make_uint4(sig[4 * k], sig[4 * k + 1], sig[4 * k + 2], sig[4 * k + 3]) : make_uint4(0, 0, 0, 0);
+}
+
 struct DeviceState {
     int device = -1;
     cudaStream_t stream = nullptr;
@@ -127,10 +150,18 @@ struct DeviceState {
 
 }  // namespace
 
+struct StageRecord {
+    int stage;
+    int device;
+    cudaEvent_t e0, e1;
+};
+
 struct jjs_ctx {
     std::vector<DeviceState> dev;
     char err[512];
     uint64_t launches;
+    bool profile;
+    std::vector<StageRecord> records;
 };
 
 namespace {
@@ -151,6 +182,26 @@ int fail(jjs_ctx* ctx, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? JJS_ERR_NOMEM : JJS_ERR_CUDA, \
                                            "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// Optional per-stage timing: CUDA events recorded on the launching stream around each stage's launches.
+struct StageTimer {
+    jjs_ctx* ctx;
+    StageRecord rec;
+    bool on;
+    StageTimer(jjs_ctx* c, int device, int stage, cudaStream_t s) : ctx(c), on(c->profile) {
+        if (!on) return;
+        rec.stage = stage;
+        rec.device = device;
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+        cudaEventRecord(rec.e0, s);
+    }
+    void stop(cudaStream_t s) {
+        if (!on) return;
+        cudaEventRecord(rec.e1, s);
+        ctx->records.push_back(rec);
+    }
+};
 
 inline unsigned blocks_for(size_t threads) { return (unsigned)((threads + BLOCK - 1) / BLOCK); }
 
@@ -220,26 +271,36 @@ int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, con
         Fields pts;
         WireField fmsg, fu;
         variant_fields(variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, pts, fmsg, fu);
+        StageTimer t0(ctx, d.device, 0, stream);
         k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, m, d.pts_u, d.pts_v, d.pflags, T);
+        t0.stop(stream);
+        StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
+        t1.stop(stream);
         ctx->launches += 2;
         if (challenge_only) {
             JJS_CUDA(ctx, cudaMemcpyAsync(c_out + off * 32, d.cwords, 32 * m, cudaMemcpyDeviceToDevice, stream));
             continue;
         }
+        StageTimer t2(ctx, d.device, 2, stream);
         for (size_t first = 0; first < slots * m; first += TAB_THREADS) {
             size_t cnt = slots * m - first < TAB_THREADS ? slots * m - first : TAB_THREADS;
             k_subgroup<<<blocks_for(cnt), BLOCK, 0, stream>>>(d.pts_u, d.pts_v, d.pflags, first, cnt, d.tab, TAB_THREADS);
             ctx->launches++;
         }
+        t2.stop(stream);
+        StageTimer t3(ctx, d.device, 3, stream);
         for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
             size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
             k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, d.iflags, m, first, cnt, fu, d.cwords,
                                                              d.eqflags, d.tab, TAB_THREADS, T);
             ctx->launches++;
         }
+        t3.stop(stream);
+        StageTimer t4(ctx, d.device, 4, stream);
         k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, status + off,
                                                        c_out ? c_out + off * 32 : nullptr);
+        t4.stop(stream);
         ctx->launches++;
     }
     JJS_CUDA(ctx, cudaGetLastError());
@@ -280,6 +341,41 @@ int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, c
     return JJS_SUCCESS;
 }
 
+int run_sign(jjs_ctx* ctx, int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, size_t n, uint8_t* pk_out,
+             uint8_t* sig_out) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
+    if (n == 0) return JJS_SUCCESS;
+    if (!sk || !rnd || !msg || !pk_out || !sig_out || (variant == VAR_VARGEN && !gsc)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    DeviceState& d = ctx->dev[0];
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    const size_t pks = pk_size(variant), sgs = sig_size(variant);
+    uint8_t* buf = nullptr;
+    const size_t chunk = n < CHUNK_ITEMS ? n : CHUNK_ITEMS;
+    JJS_CUDA(ctx, cudaMalloc(&buf, chunk * (4 * 32 + pks + sgs)));
+    uint8_t *d_sk = buf, *d_rnd = buf + 32 * chunk, *d_g = buf + 64 * chunk, *d_msg = buf + 96 * chunk, *d_pk = buf + 128 * chunk,
+            *d_sig = d_pk + pks * chunk;
+    int rc = JJS_SUCCESS;
+    for (size_t off = 0; off < n && rc == JJS_SUCCESS; off += chunk) {
+        size_t m = n - off < chunk ? n - off : chunk;
+        cudaMemcpyAsync(d_sk, sk + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        cudaMemcpyAsync(d_rnd, rnd + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        if (variant == VAR_VARGEN) cudaMemcpyAsync(d_g, gsc + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        cudaMemcpyAsync(d_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        if (variant == VAR_SINGLE) k_sign<VAR_SINGLE><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
+        else if (variant == VAR_DOUBLE) k_sign<VAR_DOUBLE><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
+        else k_sign<VAR_VARGEN><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
+        ctx->launches++;
+        cudaMemcpyAsync(pk_out + pks * off, d_pk, pks * m, cudaMemcpyDeviceToHost, d.stream);
+        cudaMemcpyAsync(sig_out + sgs * off, d_sig, sgs * m, cudaMemcpyDeviceToHost, d.stream);
+        cudaError_t e = cudaStreamSynchronize(d.stream);
+        if (e != cudaSuccess) rc = fail(ctx, JJS_ERR_CUDA, "sign batch failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(buf);
+    return rc;
+}
+
 int init_device(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaSetDevice(d.device));
     cudaDeviceProp prop;
@@ -318,7 +414,7 @@ int device_entry(jjs_ctx* ctx, int variant, int device_index, const uint8_t* pk,
     if (n == 0) return JJS_SUCCESS;
     if (!pk || !sig || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     DeviceState& d = ctx->dev[device_index];
-    return run_device(ctx, d, variant, pk, sig, msg, n, status, c_out, stream ? (cudaStream_t)stream : d.stream);
+    return run_device(ctx, d, variant, pk, sig, msg, n, status, c_out, (cudaStream_t)stream);
 }
 
 }  // namespace
@@ -334,6 +430,7 @@ JJS_API int jjs_init(const int* devices, int n_devices, jjs_ctx** out) {
     if (!ctx) return JJS_ERR_NOMEM;
     ctx->err[0] = 0;
     ctx->launches = 0;
+    ctx->profile = false;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count < 1) {
@@ -398,6 +495,33 @@ JJS_API int jjs_verify_double_device(jjs_ctx* ctx, int device_index, const uint8
 JJS_API int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk64, const uint8_t* d_sig64, const uint8_t* d_msg32,
                                      size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {
     return device_entry(ctx, VAR_VARGEN, device_index, d_pk64, d_sig64, d_msg32, n, d_status, d_c32_or_null, cuda_stream);
+}
+JJS_API void jjs_profile_enable(jjs_ctx* ctx, int on) {
+    if (ctx) ctx->profile = on != 0;
+}
+JJS_API int jjs_profile_collect(jjs_ctx* ctx, double* stage_ms, uint64_t* stage_count) {
+    if (!ctx || !stage_ms || !stage_count) return JJS_ERR_ARGUMENT;
+    for (int i = 0; i < JJS_N_STAGES; i++) { stage_ms[i] = 0; stage_count[i] = 0; }
+    for (auto& r : ctx->records) {
+        cudaSetDevice(r.device);
+        float ms = 0;
+        cudaError_t e = cudaEventSynchronize(r.e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+        if (e != cudaSuccess) {
+            ctx->records.clear();
+            return fail(ctx, JJS_ERR_CUDA, "profile collect: %s", cudaGetErrorString(e));
+        }
+        stage_ms[r.stage] += ms;
+        stage_count[r.stage]++;
+    }
+    ctx->records.clear();
+    return JJS_SUCCESS;
+}
+JJS_API int jjs_sign_batch(jjs_ctx* ctx, int variant, const uint8_t* sk32, const uint8_t* rnd32, const uint8_t* gen_scalar32_or_null,
+                           const uint8_t* msg32, size_t n, uint8_t* pk_out, uint8_t* sig_out) {
+    return run_sign(ctx, variant, sk32, rnd32, gen_scalar32_or_null, msg32, n, pk_out, sig_out);
 }
 JJS_API int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32, size_t n, uint8_t* c32) {
     if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");

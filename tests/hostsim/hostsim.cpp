@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../jubjub_schnorr_b200/csrc/sign_core.cuh"
 #include "../../jubjub_schnorr_b200/csrc/verify_core.cuh"
 namespace tables {
 #include "../../jubjub_schnorr_b200/csrc/jjs_constants_tables.h"
@@ -130,6 +131,16 @@ int hs_varbase_mul(const uint8_t* p32, const uint8_t* k32, uint8_t* out32, int f
     uint32_t o[8];
     point_to_wire(o, au, av);
     memcpy(out32, o, 32);
+    return 1;
+}
+int hs_sign(int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, uint8_t* pk_out, uint8_t* sig_out) {
+    ensure_ready();
+    uint32_t a[8], b[8], g[8] = {0}, m[8], pk[16], sig[24];
+    memcpy(a, sk, 32); memcpy(b, rnd, 32); memcpy(m, msg, 32);
+    if (gsc) memcpy(g, gsc, 32);
+    if (!sign_item(variant, a, b, g, m, pk, sig, g_tables)) return 0;
+    memcpy(pk_out, pk, variant == VAR_SINGLE ? 32 : 64);
+    memcpy(sig_out, sig, variant == VAR_DOUBLE ? 96 : 64);
     return 1;
 }
 // Whole pipeline through the same stage functions the kernels call.
