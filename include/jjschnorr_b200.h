@@ -96,6 +96,11 @@ int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk
 int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32,
                        size_t n, uint8_t* c32);
 
+/* is_torsion_free() of n wire-encoded points (reference src/keys/public.rs:160), by the production method
+ * (method 0: order-8 Tate pairing) or by the definition (method 1: [r]P == identity by scalar multiplication).
+ * out[i] = 1 / 0, or 0xff if the encoding does not decode.  Host buffers; a cross-check hook for the tests. */
+int jjs_subgroup_check(jjs_ctx* ctx, const uint8_t* points32, size_t n, int method, uint8_t* out);
+
 /* Batch key derivation + signing on device 0 of the context (used to make large
  * synthetic batches and by the tests).  For each item: pk = PublicKey::from(&sk) (reference
  * src/keys/public.rs:54-60; PublicKeyDouble / PublicKeyVarGen likewise) and sig = sk.sign(rng, msg) with the
@@ -109,7 +114,7 @@ int jjs_sign_batch(jjs_ctx* ctx, int variant, const uint8_t* sk32, const uint8_t
                    uint8_t* sig_out);
 
 /* Per-stage device timing (CUDA events on the launching stream around each pipeline stage):
- * stage 0 point decode, 1 challenge hash, 2 subgroup checks, 3 verification equations, 4 status.
+ * stage 0 point decode + subgroup test, 1 challenge hash, 2 (unused), 3 verification equations, 4 status.
  * jjs_profile_collect waits for the recorded events, adds their durations (ms) and occurrence counts per
  * stage into the two JJS_N_STAGES-long arrays, and clears the records. */
 #define JJS_N_STAGES 5

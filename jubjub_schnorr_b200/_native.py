@@ -15,7 +15,7 @@ EXPORTS = [
     "jjs_init", "jjs_destroy", "jjs_last_error", "jjs_device_count", "jjs_launch_count",
     "jjs_verify_single", "jjs_verify_double", "jjs_verify_vargen", "jjs_verify_aggregate",
     "jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device",
-    "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect",
+    "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect", "jjs_subgroup_check",
 ]
 
 _lib = None
@@ -63,5 +63,7 @@ def lib():
     L.jjs_profile_enable.restype = None
     L.jjs_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.jjs_profile_collect.restype = C.c_int
+    L.jjs_subgroup_check.argtypes = [vp, vp, sz, C.c_int, vp]
+    L.jjs_subgroup_check.restype = C.c_int
     _lib = L
     return L

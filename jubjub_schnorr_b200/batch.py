@@ -127,6 +127,13 @@ class BatchVerifier:
                     "jjs_challenge_only")
         return c
 
+    def subgroup_check(self, points32, method=0):
+        """is_torsion_free per point (1 / 0, 0xff = undecodable); method 0 Tate pairing, 1 scalar multiplication by r."""
+        pts = _u8(points32, 32, "points")
+        out = np.empty(pts.shape[0], dtype=np.uint8)
+        self._check(self._lib.jjs_subgroup_check(self._ctx, pts.ctypes.data, pts.shape[0], method, out.ctypes.data), "jjs_subgroup_check")
+        return out
+
     def sign_batch(self, variant, sk32, rnd32, msg32, gen_scalar32=None):
         """(pk bytes, sig bytes) for n items; mirrors PublicKey::from(&sk) + sk.sign(rng, msg) of the reference."""
         sk, rnd, msg = _u8(sk32, 32, "sk"), _u8(rnd32, 32, "rnd"), _u8(msg32, 32, "msg")

@@ -444,7 +444,64 @@ JJS_HD void fb_table_entry(niels& out, const fq& bu, const fq& bv, int w, int j)
     fq_mul(out.t2d, out.t2d, d2);
 }
 
-// [r] P == identity for a point given in affine coordinates (is_torsion_free)
+// is_torsion_free by the order-8 Tate pairing: E(Fq) is cyclic of order 8 r, so an affine point P != O lies in
+// the prime-order subgroup iff tau_8(T8, P) is an 8th power, i.e. g^((q-1)/8) == 1 with
+//     g = (N_T V)^4 (N_2T u)^2 (B (1 - v^2))^7,  N_S = B^2 (1+v) - c_S (1-v) u - lam_S B (1+v) u,  V = B (1+v) - x_2T (1-v)
+// (derivation and self-test against [r]P on all eight torsion cosets: tools/gen_device_constants.py, tate_constants).
+// One fixed exponentiation (~255 squarings) replaces a 252-bit scalar multiplication.  g == 0 exactly for the
+// eight torsion points (the identity included: callers flag it separately), all of which are reported "not free".
+JJS_HD bool point_is_torsion_free_tate(const fq& u, const fq& v) {
+    fq one, opv, omv, t, a, b, nT, n2T, V, h, g, k;
+    fq_one(one);
+    fq_add(opv, one, v);
+    fq_sub(omv, one, v);
+    fq_mul(a, omv, u);   // (1-v) u
+    fq_mul(b, opv, u);   // (1+v) u
+    fq_load_const(k, JJS_C(TATE)[1]);
+    fq_mul(t, opv, k);   // B^2 (1+v)
+    fq_load_const(k, JJS_C(TATE)[2]);
+    fq_mul(nT, a, k);
+    fq_sub(nT, t, nT);
+    fq_load_const(k, JJS_C(TATE)[3]);
+    fq_mul(g, b, k);
+    fq_sub(nT, nT, g);
+    fq_load_const(k, JJS_C(TATE)[4]);
+    fq_mul(n2T, a, k);
+    fq_sub(n2T, t, n2T);
+    fq_load_const(k, JJS_C(TATE)[5]);
+    fq_mul(g, b, k);
+    fq_sub(n2T, n2T, g);
+    fq_load_const(k, JJS_C(TATE)[0]);
+    fq_mul(V, opv, k);   // B (1+v)
+    fq_load_const(k, JJS_C(TATE)[6]);
+    fq_mul(g, omv, k);
+    fq_sub(V, V, g);
+    fq_mul(h, opv, omv);  // 1 - v^2
+    fq_load_const(k, JJS_C(TATE)[0]);
+    fq_mul(h, h, k);
+    fq_mul(a, nT, V);
+    fq_sqr(a, a);
+    fq_sqr(a, a);         // (N_T V)^4
+    fq_mul(b, n2T, u);
+    fq_sqr(b, b);         // (N_2T u)^2
+    fq_mul(g, a, b);
+    fq_sqr(a, h);         // h^2
+    fq_sqr(b, a);         // h^4
+    fq_mul(a, a, h);      // h^3
+    fq_mul(a, a, b);      // h^7
+    fq_mul(g, g, a);
+    // g^((q-1)/8) = (g^t)^(2^29),  g^t = g * (g^((t-1)/2))^2
+    fq w;
+    fq_pow_tm1d2(w, g);
+    fq_sqr(w, w);
+    fq_mul(w, w, g);
+#pragma unroll 1
+    for (int i = 0; i < 29; i++) fq_sqr(w, w);
+    return fq_eq(w, one);
+}
+
+// [r] P == identity for a point given in affine coordinates (is_torsion_free), by scalar multiplication.
+// Kept as the definition-level cross-check of point_is_torsion_free_tate (jjs_subgroup_check, method 1).
 JJS_HD bool point_is_torsion_free(fq* tab, size_t stride, const fq& u, const fq& v) {
     varbase_table_build(tab, stride, u, v);
     ext m;

@@ -46,11 +46,11 @@ __global__ void __launch_bounds__(BLOCK) k_challenge(int variant, const fq* pts_
     stage_challenge(variant, pts_u, pts_v, pflags, n, item, msg, usc, cwords, iflags);
 }
 
-__global__ void __launch_bounds__(BLOCK) k_subgroup(const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t first, size_t count,
-                                                    fq* tab, size_t stride) {
+__global__ void __launch_bounds__(BLOCK) k_subgroup_check(WireField pts, size_t first, size_t count, int method, uint8_t* out, fq* tab,
+                                                          size_t stride, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    stage_subgroup(pts_u, pts_v, pflags, first + t, tab + t, stride);
+    out[first + t] = subgroup_check(pts, first + t, method, tab + t, stride, T);
 }
 
 // thread t < neq * n : equation t / n of item t % n
@@ -282,13 +282,6 @@ int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, con
             JJS_CUDA(ctx, cudaMemcpyAsync(c_out + off * 32, d.cwords, 32 * m, cudaMemcpyDeviceToDevice, stream));
             continue;
         }
-        StageTimer t2(ctx, d.device, 2, stream);
-        for (size_t first = 0; first < slots * m; first += TAB_THREADS) {
-            size_t cnt = slots * m - first < TAB_THREADS ? slots * m - first : TAB_THREADS;
-            k_subgroup<<<blocks_for(cnt), BLOCK, 0, stream>>>(d.pts_u, d.pts_v, d.pflags, first, cnt, d.tab, TAB_THREADS);
-            ctx->launches++;
-        }
-        t2.stop(stream);
         StageTimer t3(ctx, d.device, 3, stream);
         for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
             size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
@@ -495,6 +488,32 @@ JJS_API int jjs_verify_double_device(jjs_ctx* ctx, int device_index, const uint8
 JJS_API int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk64, const uint8_t* d_sig64, const uint8_t* d_msg32,
                                      size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {
     return device_entry(ctx, VAR_VARGEN, device_index, d_pk64, d_sig64, d_msg32, n, d_status, d_c32_or_null, cuda_stream);
+}
+JJS_API int jjs_subgroup_check(jjs_ctx* ctx, const uint8_t* points32, size_t n, int method, uint8_t* out) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (method < 0 || method > 1) return fail(ctx, JJS_ERR_ARGUMENT, "bad method");
+    if (n == 0) return JJS_SUCCESS;
+    if (!points32 || !out) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    DeviceState& d = ctx->dev[0];
+    int rc = ensure_scratch(ctx, d);
+    if (rc) return rc;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    JJS_CUDA(ctx, cudaMalloc(&d_in, 32 * n));
+    JJS_CUDA(ctx, cudaMalloc(&d_out, n));
+    cudaMemcpyAsync(d_in, points32, 32 * n, cudaMemcpyHostToDevice, d.stream);
+    for (size_t first = 0; first < n; first += TAB_THREADS) {
+        size_t cnt = n - first < TAB_THREADS ? n - first : TAB_THREADS;
+        k_subgroup_check<<<blocks_for(cnt), BLOCK, 0, d.stream>>>(WireField{d_in, 32}, first, cnt, method, d_out, d.tab, TAB_THREADS, d.tables());
+        ctx->launches++;
+    }
+    cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "subgroup check failed: %s", cudaGetErrorString(e));
+    return JJS_SUCCESS;
 }
 JJS_API void jjs_profile_enable(jjs_ctx* ctx, int on) {
     if (ctx) ctx->profile = on != 0;

@@ -51,6 +51,7 @@ JJS_HD void stage_decode(const WireField& f, size_t item, fq* out_u, fq* out_v, 
         fq one;
         fq_one(one);
         fl = PF_DECODED | ((fq_is_zero(u) && fq_eq(v, one)) ? PF_IDENTITY : 0);
+        if (point_is_torsion_free_tate(u, v)) fl |= PF_TORSION_FREE;
         out_u[slot_index] = u;
         out_v[slot_index] = v;
     }
@@ -113,11 +114,20 @@ JJS_HD void stage_challenge(int variant, const fq* pts_u, const fq* pts_v, const
     for (int i = 0; i < 8; i++) c_out[item * 8 + i] = c[i];
 }
 
-// ---- stage 3: subgroup membership of one decoded point ------------------------------------------
-JJS_HD void stage_subgroup(const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t slot_index, fq* tab, size_t stride) {
-    uint8_t fl = pflags[slot_index];
-    if (!(fl & PF_DECODED)) return;
-    if (point_is_torsion_free(tab, stride, pts_u[slot_index], pts_v[slot_index])) pflags[slot_index] = fl | PF_TORSION_FREE;
+// ---- subgroup membership of one wire-encoded point, by either method (cross-check hook) ------------
+// returns 0xff if the encoding does not decode, else 1 / 0 for is_torsion_free()
+JJS_HD uint8_t subgroup_check(const WireField& f, size_t i, int method, fq* tab, size_t stride, const Tables& T) {
+    uint32_t w[8];
+    wire_load(w, f, i);
+    fq u, v;
+    if (!point_from_wire(u, v, w, T)) return 0xff;
+    if (method == 0) {
+        fq one;
+        fq_one(one);
+        if (fq_is_zero(u) && fq_eq(v, one)) return 1;  // the identity is torsion free by definition
+        return point_is_torsion_free_tate(u, v) ? 1 : 0;
+    }
+    return point_is_torsion_free(tab, stride, u, v) ? 1 : 0;
 }
 
 // ---- stage 4: one verification equation  u*B + c*PK == R ------------------------------------------

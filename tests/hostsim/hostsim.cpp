@@ -133,6 +133,11 @@ int hs_varbase_mul(const uint8_t* p32, const uint8_t* k32, uint8_t* out32, int f
     memcpy(out32, o, 32);
     return 1;
 }
+int hs_subgroup(const uint8_t* p32, int method) {
+    ensure_ready();
+    std::vector<fq> tab(36);
+    return subgroup_check(WireField{p32, 32}, 0, method, tab.data(), 1, g_tables);
+}
 int hs_sign(int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, uint8_t* pk_out, uint8_t* sig_out) {
     ensure_ready();
     uint32_t a[8], b[8], g[8] = {0}, m[8], pk[16], sig[24];
@@ -159,7 +164,6 @@ void hs_verify(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t
     for (int s = 0; s < slots; s++)
         for (size_t i = 0; i < n; i++) stage_decode(f[s], i, pu.data(), pv.data(), pf.data(), s * n + i, g_tables);
     for (size_t i = 0; i < n; i++) stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
-    for (size_t k = 0; k < slots * n; k++) stage_subgroup(pu.data(), pv.data(), pf.data(), k, tab.data(), 1);
     for (size_t i = 0; i < n; i++) {
         bool all = (itf[i] & IF_SCALARS_OK);
         for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);

@@ -70,3 +70,31 @@ def test_ragged_and_empty(bv):
         pk, sig, msg = co.gen_single(5, n)
         st = bv.verify_single(pk, sig, msg)
         assert st.shape == (n,) and (st == 0).all()
+
+
+def test_subgroup_tate_equals_scalar_mul_definition(bv):
+    """The production subgroup test (order-8 Tate pairing) against [r]P == identity on the GPU, over random curve
+    points in every torsion coset, the torsion points themselves and undecodable strings."""
+    rng = np.random.default_rng(17)
+    n = 1 << 15
+    pk, _, _ = co.gen_single(23, n // 8)
+    t8 = adv.torsion()[8]
+    pts = [pk]
+    cur = pk
+    for _ in range(7):  # P + j * T8
+        cur = np.stack([_a(co.point_add(cur[i].tobytes(), t8)) for i in range(cur.shape[0])])
+        pts.append(cur)
+    rand = rng.integers(0, 256, size=(4096, 32), dtype=np.uint8)  # arbitrary strings: ~half decode, any coset
+    tors = [o.point_to_bytes(o.IDENTITY)]
+    for _ in range(7):
+        tors.append(co.point_add(tors[-1], t8))
+    allp = np.concatenate(pts + [rand, np.stack([_a(x) for x in tors])])
+    a = bv.subgroup_check(allp, method=0)
+    b = bv.subgroup_check(allp, method=1)
+    assert np.array_equal(a, b)
+    assert (a[: n // 8] == 1).all() and (a[n // 8: n] == 0).all()
+    assert a[-8:].tolist() == [1, 0, 0, 0, 0, 0, 0, 0]
+    ref = np.array([co.point_is_valid(allp[i].tobytes()) for i in range(n, n + 256)])  # oracle: -1 undecodable else is_valid
+    got = a[n: n + 256].astype(np.int64)
+    got[got == 255] = -1
+    assert np.array_equal(got, ref)

@@ -210,6 +210,111 @@ def hades_scaled_model(state, sch):
     return [mm(v, sch["unscale_mont"]) * Rinv % Q for v in X]   # back to canonical integers
 
 
+# ------------------------------------------------------------------------------------------------
+# subgroup membership by the order-8 Tate pairing (cofactor 8, cyclic 2-Sylow subgroup)
+# ------------------------------------------------------------------------------------------------
+def ed_add(p, q_):
+    u1, v1 = p
+    u2, v2 = q_
+    k = D * u1 * u2 % Q * v1 * v2 % Q
+    return ((u1 * v2 + v1 * u2) * pow(1 + k, -1, Q) % Q, (v1 * v2 + u1 * u2) * pow(1 - k, -1, Q) % Q)
+
+
+def ed_mul(p, k):
+    acc = (0, 1)
+    for bit in bin(k)[2:]:
+        acc = ed_add(acc, acc)
+        if bit == "1":
+            acc = ed_add(acc, p)
+    return acc
+
+
+def tonelli(a):
+    if pow(a, (Q - 1) // 2, Q) != 1:
+        return None
+    s, t = 32, (Q - 1) >> 32
+    z = 2
+    while pow(z, (Q - 1) // 2, Q) == 1:
+        z += 1
+    c, x, b, m = pow(z, t, Q), pow(a, (t + 1) // 2, Q), pow(a, t, Q), s
+    while b != 1:
+        i, b2 = 0, b
+        while b2 != 1:
+            b2 = b2 * b2 % Q
+            i += 1
+        g = pow(c, 1 << (m - i - 1), Q)
+        x, c = x * g % Q, g * g % Q
+        b, m = b * c % Q, i
+    return x
+
+
+def tate_constants():
+    """E(Fq) is cyclic of order 8 r, so P is in the prime-order subgroup iff P is in 8 E(Fq) iff the order-8 Tate
+    pairing tau(T8, P) is an 8th power, T8 a point of exact order 8.  With the normalised Miller function
+    f = l_T^4 l_2T^2 / (v_2T^4 x) on the Weierstrass model y^2 = x^3 + A B x^2 + B^2 x (x = B (1+v)/(1-v),
+    y = B^2 (1+v)/((1-v) u)), cleared of denominators modulo 8th powers:
+        g = (N_T V)^4 (N_2T u)^2 (B (1 - v^2))^7,   N_S = B^2 (1+v) - c_S (1-v) u - lam_S B (1+v) u,   V = B (1+v) - x_2T (1-v)
+    and P is torsion free iff g^((q-1)/8) == 1.  Returns the constants and a checker used for self-test."""
+    inv = lambda x: pow(x, -1, Q)
+    a = Q - 1
+    A, B = 2 * (a + D) * inv(a - D) % Q, 4 * inv(a - D) % Q
+    a2, a4 = A * B % Q, B * B % Q
+    v = 2
+    while True:  # first curve point whose r-multiple has exact order 8
+        v += 1
+        u2 = (v * v - 1) * inv(1 + D * v * v) % Q
+        u = tonelli(u2)
+        if u is None:
+            continue
+        t8 = ed_mul((u, v), R_ORDER)
+        if ed_mul(t8, 4) != (0, 1) and ed_mul(t8, 8) == (0, 1):
+            break
+
+    def to_w(p):
+        pu, pv = p
+        X = (1 + pv) * inv(1 - pv) % Q
+        Y = (1 + pv) * inv((1 - pv) * pu) % Q
+        return (B * X % Q, B * B % Q * Y % Q)
+
+    def w_dbl(P):
+        x1, y1 = P
+        lam = (3 * x1 * x1 + 2 * a2 * x1 + a4) * inv(2 * y1) % Q
+        x3 = (lam * lam - a2 - 2 * x1) % Q
+        return (x3, (lam * (x1 - x3) - y1) % Q), lam
+
+    Tw = to_w(t8)
+    T2w, lamT = w_dbl(Tw)
+    T4w, lam2T = w_dbl(T2w)
+    assert T4w == (0, 0)
+    cT, c2T = (Tw[1] - lamT * Tw[0]) % Q, (T2w[1] - lam2T * T2w[0]) % Q
+    consts = dict(B=B, B2=B * B % Q, cT=cT, lamTB=lamT * B % Q, c2T=c2T, lam2TB=lam2T * B % Q, x2T=T2w[0])
+
+    def torsion_free(p):
+        pu, pv = p
+        opv, omv = (1 + pv) % Q, (1 - pv) % Q
+        nT = (consts["B2"] * opv - cT * omv % Q * pu - consts["lamTB"] * opv % Q * pu) % Q
+        n2T = (consts["B2"] * opv - c2T * omv % Q * pu - consts["lam2TB"] * opv % Q * pu) % Q
+        V = (B * opv - consts["x2T"] * omv) % Q
+        h = B * (1 - pv * pv) % Q
+        g = pow(nT * V, 4, Q) * pow(n2T * pu, 2, Q) % Q * pow(h, 7, Q) % Q
+        return pow(g, (Q - 1) // 8, Q) == 1
+
+    # self-test on every coset of the 8-torsion
+    import random
+    rnd = random.Random(7)
+    for _ in range(6):
+        p = ed_mul(G, rnd.randrange(1, R_ORDER))
+        cur = p
+        for j in range(8):
+            assert torsion_free(cur) == (j == 0), "Tate subgroup test disagrees with the definition"
+            cur = ed_add(cur, t8)
+    cur = (0, 1)
+    for j in range(8):  # the torsion points themselves (identity reported as not torsion free: it is rejected anyway)
+        assert not torsion_free(cur)
+        cur = ed_add(cur, t8)
+    return consts
+
+
 def signed_radix16(k, n=64):
     ds, carry = [], 0
     for i in range(n):
@@ -226,6 +331,7 @@ def signed_radix16(k, n=64):
 def main():
     sq = sqrt_constants()
     sch = hades_schedule()
+    tate = tate_constants()
     for st in ([1, 2, 3, 4, 5], [0] * 5, [Q - 1, 7, Q - 2, 12345678901234567890, 1 << 200]):
         assert hades_scaled_model(st, sch) == hades_reference(st), "scaled Hades model disagrees with the reference form"
     U, T = [], []
@@ -242,6 +348,8 @@ def main():
     u("JJS_CONST_QUAL uint32_t GEN_UV[2][8] = {%s, %s}; /* GENERATOR_EXTENDED affine, Montgomery */" % (limbs(mont(G[0])), limbs(mont(G[1]))))
     u("JJS_CONST_QUAL uint32_t GEN_NUMS_UV[2][8] = {%s, %s}; /* GENERATOR_NUMS_EXTENDED */" % (limbs(mont(G_NUMS[0])), limbs(mont(G_NUMS[1]))))
     u("JJS_CONST_QUAL uint32_t Q_MINUS_2[8] = %s;" % limbs(Q - 2))
+    u("/* order-8 Tate pairing subgroup test (see tate_constants in the generator), Montgomery: B, B^2, c_T, lam_T B, c_2T, lam_2T B, x_2T */")
+    u("JJS_CONST_QUAL uint32_t TATE[7][8] = {%s};" % ", ".join(limbs(mont(tate[k])) for k in ("B", "B2", "cT", "lamTB", "c2T", "lam2TB", "x2T")))
     u("#define JJS_SQRT_SCHED_LEN %d" % len(sq["sched"]))
     u("JJS_CONST_QUAL uint8_t SQRT_SCHED[JJS_SQRT_SCHED_LEN][2] = {%s}; /* (squarings, odd-power index | 0xff) for a^((t-1)/2) */"
       % ", ".join("{%d, %d}" % s_ for s_ in sq["sched"]))
