@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libjjschnorr_b200.so")
+LIB_PATH = os.environ.get("JJS_B200_LIB", os.path.join(_DIR, "libjjschnorr_b200.so"))  # override: A/B builds of the same ABI
 
 EXPORTS = [
     "jjs_init", "jjs_destroy", "jjs_last_error", "jjs_device_count", "jjs_launch_count",

@@ -31,7 +31,7 @@ namespace jjs {
 // -q^-1 mod 2^32 = 0xffffffff, so the Montgomery quotient digit is just the negated low limb.
 #define JJS_Q_LIMBS {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u}
 
-struct fq {
+struct alignas(16) fq {
     uint32_t l[8];
 };
 
@@ -237,63 +237,81 @@ JJS_HD void add_q_masked(uint32_t* r, const uint32_t* x, uint32_t mask) {
 //     n[0..8]= ev[2..8],inject  + m*(q1,q3,q5,q7)  (new odd accumulator, limbs 1..9)
 //     od[1..8]+= m*(q0,q2,q4,q6) with e0 + m*q0 == 0 (mod 2^32)   (new even accumulator is (0, od[1..8]))
 JJS_HD void redc_step(const uint32_t* ev, uint32_t* od, uint32_t* n, uint32_t inject) {
+    // The two low limbs of q are 1 and 2^32 - 1, so their products with m need no multiplier:
+    //   m * q0 = m                 -> e0 + m == 0 (mod 2^32) with carry (e0 != 0)
+    //   m * q1 = (m - [m != 0]) * 2^32 + e0     (because -m == e0 mod 2^32)
+    // which leaves 6 wide multiplies per step on the integer-multiply pipe instead of 8.
 #if defined(__CUDA_ARCH__)
-    uint32_t e0, m;
-    asm("add.cc.u32 %0, %11, %12;\n\t"
-        "sub.u32 %1, 0, %0;\n\t"
-        "madc.lo.cc.u32 %2, %1, 0xffffffff, %13;\n\t"
-        "madc.hi.cc.u32 %3, %1, 0xffffffff, %14;\n\t"
-        "madc.lo.cc.u32 %4, %1, 0x53bda402, %15;\n\t"
-        "madc.hi.cc.u32 %5, %1, 0x53bda402, %16;\n\t"
-        "madc.lo.cc.u32 %6, %1, 0x3339d808, %17;\n\t"
-        "madc.hi.cc.u32 %7, %1, 0x3339d808, %18;\n\t"
-        "madc.lo.cc.u32 %8, %1, 0x73eda753, %19;\n\t"
-        "madc.hi.cc.u32 %9, %1, 0x73eda753, %20;\n\t"
-        "addc.u32 %10, 0, 0;"
-        : "=&r"(e0), "=&r"(m), "=&r"(n[0]), "=&r"(n[1]), "=&r"(n[2]), "=&r"(n[3]), "=&r"(n[4]), "=&r"(n[5]), "=&r"(n[6]),
-          "=&r"(n[7]), "=&r"(n[8])
-        : "r"(od[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]),
-          "r"(inject));
-    asm("mad.lo.cc.u32 %0, %9, 0x00000001, %0;\n\t"
-        "madc.hi.cc.u32 %1, %9, 0x00000001, %1;\n\t"
-        "madc.lo.cc.u32 %2, %9, 0xfffe5bfe, %2;\n\t"
-        "madc.hi.cc.u32 %3, %9, 0xfffe5bfe, %3;\n\t"
-        "madc.lo.cc.u32 %4, %9, 0x09a1d805, %4;\n\t"
-        "madc.hi.cc.u32 %5, %9, 0x09a1d805, %5;\n\t"
-        "madc.lo.cc.u32 %6, %9, 0x299d7d48, %6;\n\t"
-        "madc.hi.cc.u32 %7, %9, 0x299d7d48, %7;\n\t"
-        "addc.u32 %8, %8, 0;"
-        : "+r"(e0), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8])
-        : "r"(m));
-    od[0] = e0;  // == 0
+    uint32_t e0, c0, m, h1;  // h1, c0: scratch of the asm blocks
+    asm("add.cc.u32 %9, %13, %14;\n\t"          // e0 = od0 + ev1, CF feeds the odd chain
+        "sub.u32 %10, 0, %9;\n\t"               // m = -e0
+        "min.u32 %11, %10, 1;\n\t"
+        "sub.u32 %11, %10, %11;\n\t"            // h1 = m - [m != 0]
+        "addc.cc.u32 %0, %15, %9;\n\t"          // n0 = ev2 + e0 + CF
+        "addc.cc.u32 %1, %16, %11;\n\t"         // n1 = ev3 + h1 + CF
+        "madc.lo.cc.u32 %2, %10, 0x53bda402, %17;\n\t"
+        "madc.hi.cc.u32 %3, %10, 0x53bda402, %18;\n\t"
+        "madc.lo.cc.u32 %4, %10, 0x3339d808, %19;\n\t"
+        "madc.hi.cc.u32 %5, %10, 0x3339d808, %20;\n\t"
+        "madc.lo.cc.u32 %6, %10, 0x73eda753, %21;\n\t"
+        "madc.hi.cc.u32 %7, %10, 0x73eda753, %22;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(n[0]), "=&r"(n[1]), "=&r"(n[2]), "=&r"(n[3]), "=&r"(n[4]), "=&r"(n[5]), "=&r"(n[6]), "=&r"(n[7]), "=&r"(n[8]),
+          "=&r"(e0), "=&r"(m), "=&r"(h1), "=&r"(c0)
+        : "r"(od[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(inject));
+    // even chain: limb 0 cancels (e0 + m), its carry is (e0 != 0) == (m != 0)
+    asm("add.cc.u32 %8, %9, %10;\n\t"           // e0 + m -> 0, CF = (e0 != 0)
+        "addc.cc.u32 %0, %0, 0;\n\t"
+        "madc.lo.cc.u32 %1, %10, 0xfffe5bfe, %1;\n\t"
+        "madc.hi.cc.u32 %2, %10, 0xfffe5bfe, %2;\n\t"
+        "madc.lo.cc.u32 %3, %10, 0x09a1d805, %3;\n\t"
+        "madc.hi.cc.u32 %4, %10, 0x09a1d805, %4;\n\t"
+        "madc.lo.cc.u32 %5, %10, 0x299d7d48, %5;\n\t"
+        "madc.hi.cc.u32 %6, %10, 0x299d7d48, %6;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "=&r"(c0)
+        : "r"(e0), "r"(m));
+    od[0] = 0;
+    (void)h1;
+    (void)c0;
 #else
     constexpr uint32_t Q[8] = JJS_Q_LIMBS;
     uint64_t s = (uint64_t)od[0] + ev[1];
     uint32_t e0 = (uint32_t)s;
     uint64_t c = s >> 32;
     uint32_t m = 0u - e0;
-    const uint32_t addend[8] = {ev[2], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8], inject};
-    for (int k = 0; k < 4; k++) {
-        uint64_t p = (uint64_t)m * Q[2 * k + 1];
+    uint32_t h1 = m - (m != 0u ? 1u : 0u);
+    // odd chain
+    uint64_t t = (uint64_t)ev[2] + e0 + c;
+    n[0] = (uint32_t)t;
+    t = (uint64_t)ev[3] + h1 + (t >> 32);
+    n[1] = (uint32_t)t;
+    c = t >> 32;
+    const uint32_t addend[6] = {ev[4], ev[5], ev[6], ev[7], ev[8], inject};
+    for (int k = 0; k < 3; k++) {
+        uint64_t p = (uint64_t)m * Q[2 * k + 3];
         uint64_t lo = (uint64_t)addend[2 * k] + (uint32_t)p + c;
-        n[2 * k] = (uint32_t)lo;
+        n[2 * k + 2] = (uint32_t)lo;
         uint64_t hi = (uint64_t)addend[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
-        n[2 * k + 1] = (uint32_t)hi;
+        n[2 * k + 3] = (uint32_t)hi;
         c = hi >> 32;
     }
     n[8] = (uint32_t)c;
-    c = 0;
-    uint32_t* acc[8] = {&e0, &od[1], &od[2], &od[3], &od[4], &od[5], &od[6], &od[7]};
-    for (int k = 0; k < 4; k++) {
-        uint64_t p = (uint64_t)m * Q[2 * k];
-        uint64_t lo = (uint64_t)*acc[2 * k] + (uint32_t)p + c;
-        *acc[2 * k] = (uint32_t)lo;
-        uint64_t hi = (uint64_t)*acc[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
-        *acc[2 * k + 1] = (uint32_t)hi;
+    // even chain
+    c = (e0 != 0u) ? 1 : 0;
+    t = (uint64_t)od[1] + c;
+    od[1] = (uint32_t)t;
+    c = t >> 32;
+    for (int k = 0; k < 3; k++) {
+        uint64_t p = (uint64_t)m * Q[2 * k + 2];
+        uint64_t lo = (uint64_t)od[2 * k + 2] + (uint32_t)p + c;
+        od[2 * k + 2] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)od[2 * k + 3] + (uint32_t)(p >> 32) + (lo >> 32);
+        od[2 * k + 3] = (uint32_t)hi;
         c = hi >> 32;
     }
     od[8] += (uint32_t)c;
-    od[0] = e0;
+    od[0] = 0;
 #endif
 }
 

@@ -24,6 +24,12 @@ using namespace jjs;
 namespace {
 
 constexpr int BLOCK = 128;
+#ifndef JJS_EQ_MINBLOCKS
+#define JJS_EQ_MINBLOCKS 3
+#endif
+#ifndef JJS_DEC_MINBLOCKS
+#define JJS_DEC_MINBLOCKS 4
+#endif
 constexpr size_t CHUNK_ITEMS = size_t(1) << 20;   // items per pipeline pass
 constexpr size_t TAB_THREADS = size_t(1) << 21;   // threads served by the per-thread table scratch (1152 B each)
 
@@ -31,7 +37,7 @@ struct Fields {
     WireField f[4];
 };
 
-__global__ void __launch_bounds__(BLOCK) k_decode(Fields fields, int slots, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags, Tables T) {
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode(Fields fields, int slots, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)slots * n) return;
     int slot = (int)(t / n);
@@ -39,7 +45,7 @@ __global__ void __launch_bounds__(BLOCK) k_decode(Fields fields, int slots, size
     stage_decode(fields.f[slot], item, pts_u, pts_v, pflags, t, T);
 }
 
-__global__ void __launch_bounds__(BLOCK) k_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n,
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n,
                                                      WireField msg, WireField usc, uint32_t* cwords, uint8_t* iflags) {
     size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n) return;
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(BLOCK) k_subgroup_check(WireField pts, size_t 
 }
 
 // thread t < neq * n : equation t / n of item t % n
-__global__ void __launch_bounds__(BLOCK) k_equation(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags,
+__global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags,
                                                     const uint8_t* iflags, size_t n, size_t first, size_t count, WireField usc,
                                                     const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
