@@ -37,12 +37,29 @@ struct Fields {
     WireField f[4];
 };
 
-__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode(Fields fields, int slots, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags, Tables T) {
+// thread t < slots * n decodes point field t / n of item t % n into index (slot_base + t / n) * n + t % n
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode(Fields fields, int slots, int slot_base, size_t n, fq* pts_u, fq* pts_v,
+                                                                      uint8_t* pflags, Tables T, bool want_subgroup) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)slots * n) return;
     int slot = (int)(t / n);
     size_t item = t - (size_t)slot * n;
-    stage_decode(fields.f[slot], item, pts_u, pts_v, pflags, t, T);
+    stage_decode(fields.f[slot], item, pts_u, pts_v, pflags, (size_t)(slot_base + slot) * n + item, T, want_subgroup);
+}
+
+// one thread folds the signer keys of one item into its aggregate key (slot 0 of the single-variant point arrays)
+__global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, const uint32_t* offsets,
+                                                     uint32_t key_base, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags, uint8_t* agg_out, fq* tab,
+                                                     size_t stride) {
+    size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n) return;
+    uint32_t w[8];
+    stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + item, stride);
+    if (agg_out) {
+        uint4* o = reinterpret_cast<uint4*>(agg_out + item * 32);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
 }
 
 __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n,
@@ -148,6 +165,11 @@ struct DeviceState {
     fq *pts_u = nullptr, *pts_v = nullptr, *tab = nullptr;
     uint8_t *pflags = nullptr, *iflags = nullptr, *eqflags = nullptr;
     uint32_t* cwords = nullptr;
+    // decoded signer keys of the aggregate-key path (grown on demand)
+    fq *keys_u = nullptr, *keys_v = nullptr;
+    uint8_t *kflags = nullptr, *s_keys = nullptr, *s_agg = nullptr;
+    uint32_t* s_offsets = nullptr;
+    size_t cap_keys = 0;
     // staging for the host-buffer entry points
     uint8_t *s_pk = nullptr, *s_sig = nullptr, *s_msg = nullptr, *s_status = nullptr, *s_c = nullptr;
     size_t stage_items = 0;
@@ -278,7 +300,7 @@ int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, con
         WireField fmsg, fu;
         variant_fields(variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, pts, fmsg, fu);
         StageTimer t0(ctx, d.device, 0, stream);
-        k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, m, d.pts_u, d.pts_v, d.pflags, T);
+        k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, 0, m, d.pts_u, d.pts_v, d.pflags, T, true);
         t0.stop(stream);
         StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
@@ -338,6 +360,90 @@ int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, c
         JJS_CUDA(ctx, cudaStreamSynchronize(ctx->dev[k].stream));
     }
     return JJS_SUCCESS;
+}
+
+// aggregate_pk(..).verify(..) for a contiguous range of items on one device (host buffers; joined by the caller)
+int run_aggregate_shard(jjs_ctx* ctx, DeviceState& d, const uint8_t* pks, const uint32_t* offsets, const uint8_t* sig, const uint8_t* msg, size_t n,
+                        uint8_t* status, uint8_t* c_out, uint8_t* agg_out) {
+    int rc = ensure_scratch(ctx, d);
+    if (rc) return rc;
+    rc = ensure_staging(ctx, d, n < CHUNK_ITEMS ? n : CHUNK_ITEMS);
+    if (rc) return rc;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    Tables T = d.tables();
+    cudaStream_t stream = d.stream;
+    for (size_t off = 0; off < n; off += CHUNK_ITEMS) {
+        size_t m = n - off < CHUNK_ITEMS ? n - off : CHUNK_ITEMS;
+        uint32_t key_lo = offsets[off], key_hi = offsets[off + m];
+        size_t K = key_hi - key_lo;
+        if (K > d.cap_keys) {
+            JJS_CUDA(ctx, cudaStreamSynchronize(stream));
+            cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.s_keys);
+            d.keys_u = d.keys_v = nullptr; d.kflags = d.s_keys = nullptr; d.cap_keys = 0;
+            JJS_CUDA(ctx, cudaMalloc(&d.keys_u, sizeof(fq) * K));
+            JJS_CUDA(ctx, cudaMalloc(&d.keys_v, sizeof(fq) * K));
+            JJS_CUDA(ctx, cudaMalloc(&d.kflags, K));
+            JJS_CUDA(ctx, cudaMalloc(&d.s_keys, 32 * K));
+            d.cap_keys = K;
+        }
+        if (!d.s_offsets) {
+            JJS_CUDA(ctx, cudaMalloc(&d.s_offsets, sizeof(uint32_t) * (CHUNK_ITEMS + 1)));
+            JJS_CUDA(ctx, cudaMalloc(&d.s_agg, 32 * CHUNK_ITEMS));
+        }
+        if (K) JJS_CUDA(ctx, cudaMemcpyAsync(d.s_keys, pks + 32 * (size_t)key_lo, 32 * K, cudaMemcpyHostToDevice, stream));
+        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_offsets, offsets + off, sizeof(uint32_t) * (m + 1), cudaMemcpyHostToDevice, stream));
+        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_sig, sig + 64 * off, 64 * m, cudaMemcpyHostToDevice, stream));
+        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, stream));
+        Fields fk, fr;
+        fk.f[0] = WireField{d.s_keys, 32};
+        fr.f[0] = WireField{d.s_sig + 32, 64};
+        fk.f[1] = fk.f[2] = fk.f[3] = fr.f[1] = fr.f[2] = fr.f[3] = WireField{nullptr, 0};
+        WireField fmsg{d.s_msg, 32}, fu{d.s_sig, 64};
+        if (K) k_decode<<<blocks_for(K), BLOCK, 0, stream>>>(fk, 1, 0, K, d.keys_u, d.keys_v, d.kflags, T, false);
+        for (size_t first = 0; first < m; first += TAB_THREADS) {  // m <= CHUNK_ITEMS <= TAB_THREADS: one launch
+            size_t cnt = m - first < TAB_THREADS ? m - first : TAB_THREADS;
+            k_aggregate<<<blocks_for(cnt), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d.s_offsets, key_lo, m, d.pts_u, d.pts_v, d.pflags,
+                                                              agg_out ? d.s_agg : nullptr, d.tab, TAB_THREADS);
+        }
+        k_decode<<<blocks_for(m), BLOCK, 0, stream>>>(fr, 1, 1, m, d.pts_u, d.pts_v, d.pflags, T, true);
+        k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
+        k_equation<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, d.iflags, m, 0, m, fu, d.cwords, d.eqflags, d.tab,
+                                                       TAB_THREADS, T);
+        k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d.s_status, c_out ? d.s_c : nullptr);
+        ctx->launches += 6;
+        JJS_CUDA(ctx, cudaGetLastError());
+        JJS_CUDA(ctx, cudaMemcpyAsync(status + off, d.s_status, m, cudaMemcpyDeviceToHost, stream));
+        if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + 32 * off, d.s_c, 32 * m, cudaMemcpyDeviceToHost, stream));
+        if (agg_out) JJS_CUDA(ctx, cudaMemcpyAsync(agg_out + 32 * off, d.s_agg, 32 * m, cudaMemcpyDeviceToHost, stream));
+        if (off + m < n) JJS_CUDA(ctx, cudaStreamSynchronize(stream));  // staging buffers are reused by the next chunk
+    }
+    return JJS_SUCCESS;
+}
+
+int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status,
+                  uint8_t* c_out, uint8_t* agg_out) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (n == 0) return JJS_SUCCESS;
+    if (!offsets || !sig || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, JJS_ERR_ARGUMENT, "offsets must be non-decreasing");
+    if (offsets[n] > offsets[0] && !pks) return fail(ctx, JJS_ERR_ARGUMENT, "null key buffer");
+    const size_t g = ctx->dev.size();
+    const size_t per = (n + g - 1) / g;
+    int rc = JJS_SUCCESS;
+    for (size_t k = 0; k < g && rc == JJS_SUCCESS; k++) {
+        size_t lo = k * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        rc = run_aggregate_shard(ctx, ctx->dev[k], pks, offsets + lo, sig + 64 * lo, msg + 32 * lo, hi - lo, status + lo,
+                                 c_out ? c_out + 32 * lo : nullptr, agg_out ? agg_out + 32 * lo : nullptr);
+    }
+    for (size_t k = 0; k < g; k++) {
+        cudaSetDevice(ctx->dev[k].device);
+        cudaError_t e = cudaStreamSynchronize(ctx->dev[k].stream);
+        if (e != cudaSuccess && rc == JJS_SUCCESS) rc = fail(ctx, JJS_ERR_CUDA, "aggregate verify failed: %s", cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 int run_sign(jjs_ctx* ctx, int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, size_t n, uint8_t* pk_out,
@@ -402,6 +508,7 @@ void free_device(DeviceState& d) {
     cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
     cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords);
     cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
+    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.s_keys); cudaFree(d.s_agg); cudaFree(d.s_offsets);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
@@ -479,9 +586,9 @@ JJS_API int jjs_verify_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* 
                               uint8_t* c32_or_null) {
     return run_host(ctx, VAR_VARGEN, pk64, sig64, msg32, n, status, c32_or_null);
 }
-JJS_API int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t*, const uint32_t*, const uint8_t*, const uint8_t*, size_t, uint8_t*, uint8_t*,
-                                 uint8_t*) {
-    return fail(ctx, JJS_ERR_ARGUMENT, "jjs_verify_aggregate: not implemented yet");
+JJS_API int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* offsets, const uint8_t* sig64, const uint8_t* msg32, size_t n,
+                                 uint8_t* status, uint8_t* c32_or_null, uint8_t* aggpk32_or_null) {
+    return run_aggregate(ctx, pks32, offsets, sig64, msg32, n, status, c32_or_null, aggpk32_or_null);
 }
 JJS_API int jjs_verify_single_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk32, const uint8_t* d_sig64, const uint8_t* d_msg32,
                                      size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {

@@ -41,7 +41,7 @@ JJS_HD int variant_slots(int variant) { return variant == VAR_SINGLE ? 2 : (vari
 
 // ---- stage 1: decode one point ---------------------------------------------------------------
 JJS_HD void stage_decode(const WireField& f, size_t item, fq* out_u, fq* out_v, uint8_t* out_flags, size_t slot_index,
-                         const Tables& T) {
+                         const Tables& T, bool want_subgroup = true) {
     uint32_t w[8];
     wire_load(w, f, item);
     fq u, v;
@@ -51,7 +51,7 @@ JJS_HD void stage_decode(const WireField& f, size_t item, fq* out_u, fq* out_v, 
         fq one;
         fq_one(one);
         fl = PF_DECODED | ((fq_is_zero(u) && fq_eq(v, one)) ? PF_IDENTITY : 0);
-        if (point_is_torsion_free_tate(u, v)) fl |= PF_TORSION_FREE;
+        if (want_subgroup && point_is_torsion_free_tate(u, v)) fl |= PF_TORSION_FREE;
         out_u[slot_index] = u;
         out_v[slot_index] = v;
     }
@@ -157,6 +157,60 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
     ext sum;
     ext_add_pniels<false>(sum, acc, nb);
     return ext_eq_affine(sum, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
+}
+
+// ---- aggregate key: multisig::aggregate_pk (reference src/multisig.rs:154-156, 393-429) ---------------
+// keys_u / keys_v / kflags: decoded signer keys of the whole batch (ragged, item i owns [offsets[i], offsets[i+1]));
+// d_j = H_trunc(pk_j || pk_0 .. pk_{n-1}),  agg = sum_j d_j * pk_j.  Like the reference, the signer keys are NOT
+// validated (only decoded); the aggregate is then treated exactly as the PublicKey of a single verification: its
+// affine coordinates, validity flags (identity, torsion freeness) and wire encoding are written to slot `out_index`.
+JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
+                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride) {
+    bool decoded = true;
+    for (uint32_t j = lo; j < hi; j++) decoded = decoded && (kflags[j] & PF_DECODED);
+    uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!decoded || 2 + 2 * (hi - lo) > JJS_MAX_ABSORB) {
+        out_flags[out_index] = 0;
+        if (agg_wire)
+            for (int i = 0; i < 8; i++) agg_wire[i] = zero[i];
+        return;
+    }
+    ext acc;
+    ext_identity(acc);
+#pragma unroll 1
+    for (uint32_t j = lo; j < hi; j++) {
+        Sponge sp;
+        sponge_start(sp, (int)(2 + 2 * (hi - lo)));
+        sponge_absorb(sp, keys_u[j]);
+        sponge_absorb(sp, keys_v[j]);
+#pragma unroll 1
+        for (uint32_t k = lo; k < hi; k++) {
+            sponge_absorb(sp, keys_u[k]);
+            sponge_absorb(sp, keys_v[k]);
+        }
+        uint32_t d[8];
+        sponge_squeeze_truncated(d, sp);
+        int8_t digits[64];
+        recode_signed16(digits, d);
+        varbase_table_build(tab, stride, keys_u[j], keys_v[j]);
+        ext term, sum;
+        varbase_mul<true>(term, tab, stride, digits);
+        pniels nt;
+        ext_to_pniels(nt, term);
+        ext_add_pniels<true>(sum, acc, nt);
+        acc = sum;
+    }
+    fq zi, u, v, one;
+    fq_inv(zi, acc.Z);
+    fq_mul(u, acc.X, zi);
+    fq_mul(v, acc.Y, zi);
+    fq_one(one);
+    uint8_t fl = PF_DECODED | ((fq_is_zero(u) && fq_eq(v, one)) ? PF_IDENTITY : 0);
+    if (point_is_torsion_free_tate(u, v)) fl |= PF_TORSION_FREE;
+    out_u[out_index] = u;
+    out_v[out_index] = v;
+    out_flags[out_index] = fl;
+    if (agg_wire) point_to_wire(agg_wire, u, v);
 }
 
 // ---- stage 5: combine flags into the reference's result -----------------------------------------

@@ -133,6 +133,28 @@ int hs_varbase_mul(const uint8_t* p32, const uint8_t* k32, uint8_t* out32, int f
     memcpy(out32, o, 32);
     return 1;
 }
+// aggregate-key verification through the stage functions (ragged keys)
+void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status,
+                         uint8_t* c_out, uint8_t* agg_out) {
+    ensure_ready();
+    size_t K = offsets[n];
+    std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(36);
+    std::vector<uint8_t> kf(K), pf(2 * n), itf(n);
+    std::vector<uint32_t> cw(8 * n);
+    WireField fk{pks, 32}, fR{sig + 32, 64}, fmsg{msg, 32}, fu{sig, 64};
+    for (size_t k = 0; k < K; k++) stage_decode(fk, k, ku.data(), kv.data(), kf.data(), k, g_tables);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t w[8];
+        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1);
+        memcpy(agg_out + 32 * i, w, 32);
+        stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables);
+        stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
+        bool all = (itf[i] & IF_SCALARS_OK) && (pf[i] & PF_DECODED) && (pf[n + i] & PF_DECODED);
+        if (all && stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
+        status[i] = stage_status(VAR_SINGLE, pf.data(), itf[i], n, i);
+        if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
+    }
+}
 int hs_subgroup(const uint8_t* p32, int method) {
     ensure_ready();
     std::vector<fq> tab(36);
