@@ -1,0 +1,78 @@
+"""The C-ABI library loads on a CPU-only machine, exports every symbol include/*.h declares, and refuses to work
+without a CUDA device (no CPU fallback).  Also checks the generated constants and the synthetic workload classes."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from oracle import c_oracle as co
+from oracle import jjs_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = []
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            src = open(os.path.join(ROOT, "include", fn)).read()
+            names += re.findall(r"\b(jjs_[a-z_0-9]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    entry.build_cuda()
+    from jubjub_schnorr_b200 import _native
+    lib = _native.lib()
+    declared = _declared()
+    assert len(declared) >= 15
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(_native.EXPORTS) == declared
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from jubjub_schnorr_b200 import BatchVerifier, JjsError
+    with pytest.raises(JjsError, match="no CUDA device"):
+        BatchVerifier([0])
+
+
+def test_product_package_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "jubjub_schnorr_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "oracle" not in text.lower() or f == "workload.py" and "No oracle" in text, f
+
+
+def test_generated_constants_match_oracle():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen", os.path.join(ROOT, "tools", "gen_device_constants.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    assert gen.round_constants() == o.ROUND_CONSTANTS and gen.mds_matrix() == o.MDS
+    assert gen.safe_tag(5) == o.safe_tag(5) and gen.safe_tag(10) == o.safe_tag(10)
+    sch = gen.hades_schedule()
+    for st in ([1, 2, 3, 4, 5], [o.Q - 1, 0, 5, 1 << 250, 77]):
+        assert gen.hades_scaled_model(st, sch) == o.hades_permute(st)
+    hdr = open(os.path.join(ROOT, "jubjub_schnorr_b200", "csrc", "jjs_constants_uniform.h")).read()
+    first = "0x%08xu" % (sch["first_ark"][0] & 0xFFFFFFFF)
+    assert first in hdr, "jjs_constants_uniform.h is stale: run tools/gen_device_constants.py"
+
+
+@pytest.mark.parametrize("variant,gen,ver", [(0, co.gen_single, co.verify_single), (1, co.gen_double, co.verify_double),
+                                             (2, co.gen_vargen, co.verify_vargen)])
+def test_workload_classes_have_the_stated_status(variant, gen, ver):
+    from jubjub_schnorr_b200 import workload as wl
+    pk, sig, msg = gen(1, 640)
+    pk, sig, msg, exp, cls = wl.invalidate(variant, pk, sig, msg, 0.25, seed=0x5A0CE)
+    st, _ = ver(pk, sig, msg)
+    assert np.array_equal(st, exp)
+    assert set(np.unique(cls).tolist()) == set(range(-1, len(wl.CLASSES)))

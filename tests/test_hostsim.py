@@ -1,0 +1,199 @@
+"""CPU twins of the device algorithms (tests/hostsim, built from the very headers the CUDA kernels use) against the
+pinned oracle: limb arithmetic and the Montgomery schedule, table square root, scaled Hades permutation, point
+decoding, fixed/variable-base multiplication, Tate subgroup test, signing, and the whole verify pipeline on
+adversarial batches.  The PTX blocks themselves are covered by the `-m gpu` parity tests."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from oracle import c_oracle as co
+from oracle import jjs_oracle as o
+from tests import adversarial as adv
+
+Q, R256 = o.Q, 1 << 256
+
+
+@pytest.fixture(scope="module")
+def L():
+    return C.CDLL(entry.build_hostsim())
+
+
+def arr(x, n=8):
+    return (C.c_uint32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+
+def val(a):
+    return sum(int(v) << (32 * i) for i, v in enumerate(a))
+
+
+def _cases(rnd, n):
+    specials = [0, 1, Q - 1, Q - 2, 2**256 - 1, 2**255, (1 << 32) - 1, Q >> 1, R256 % Q]
+    for a in specials:
+        for b in specials:
+            yield a, b
+    for _ in range(n):
+        yield rnd.getrandbits(256), rnd.getrandbits(256)
+
+
+def test_wide_products_and_reduction(L):
+    rnd = random.Random(1)
+    rinv = pow(R256, -1, Q)
+    for a, b in _cases(rnd, 4000):
+        t = (C.c_uint32 * 16)()
+        L.hs_mul_wide(arr(a), arr(b), t)
+        assert val(t) == a * b
+        L.hs_sqr_wide(arr(a), t)
+        assert val(t) == a * a
+    for t in [0, (Q << 256) - 1, (Q - 1) * (Q - 1), (1 << 256) - 1, Q * ((1 << 256) - 1)] + [rnd.randrange(Q << 256) for _ in range(4000)]:
+        r = (C.c_uint32 * 8)()
+        L.hs_redc(arr(t, 16), r)
+        assert val(r) == t * rinv % Q
+
+
+def test_field_ops(L):
+    rnd = random.Random(2)
+    rinv = pow(R256, -1, Q)
+    r = (C.c_uint32 * 8)()
+    for a, b in _cases(rnd, 3000):
+        a %= Q
+        b %= Q
+        L.hs_fq_mul(arr(a), arr(b), r); assert val(r) == a * b * rinv % Q
+        L.hs_fq_sqr(arr(a), r); assert val(r) == a * a * rinv % Q
+        L.hs_fq_add(arr(a), arr(b), r); assert val(r) == (a + b) % Q
+        L.hs_fq_sub(arr(a), arr(b), r); assert val(r) == (a - b) % Q
+        L.hs_fq_to_mont(arr(a), r); assert val(r) == a * R256 % Q
+        L.hs_fq_from_mont(arr(a), r); assert val(r) == a * rinv % Q
+    for _ in range(10):
+        a = rnd.randrange(1, Q)
+        L.hs_fq_inv(arr(a * R256 % Q), r)
+        assert val(r) == pow(a, -1, Q) * R256 % Q
+
+
+def test_sqrt_ratio(L):
+    rnd = random.Random(3)
+    rinv = pow(R256, -1, Q)
+    r = (C.c_uint32 * 8)()
+    for i in range(120):
+        num, den = rnd.randrange(Q), rnd.randrange(1, Q)
+        if i < 5:
+            num, den = [0, 1, Q - 1, 4, 9][i], [5, 1, 1, 1, 4][i]
+        ok = L.hs_sqrt_ratio(arr(num * R256 % Q), arr(den * R256 % Q), r)
+        ratio = num * pow(den, -1, Q) % Q
+        assert bool(ok) == (ratio == 0 or pow(ratio, (Q - 1) // 2, Q) == 1)
+        if ok:
+            x = val(r) * rinv % Q
+            assert x * x % Q == ratio
+
+
+def test_hades_permutation(L):
+    rnd = random.Random(4)
+    for st in ([1, 2, 3, 4, 5], [0] * 5, [Q - 1] * 5, [rnd.randrange(Q) for _ in range(5)]):
+        buf = (C.c_uint32 * 40)(*[(x >> (32 * i)) & 0xFFFFFFFF for x in st for i in range(8)])
+        L.hs_hades_permute(buf)
+        assert [val(buf[8 * i:8 * i + 8]) for i in range(5)] == o.hades_permute(st)
+
+
+def test_point_decode(L):
+    rnd = random.Random(5)
+    encs = [rnd.randbytes(32) for _ in range(80)] + [o.point_to_bytes(o.IDENTITY), adv.ORDER2_ENC, o.le32(o.Q), o.le32(o.Q - 1),
+                                                     bytes([1] + [0] * 30 + [0x80]), bytes(32), bytes([0] * 31 + [0x80])]
+    for enc in encs:
+        out = (C.c_uint32 * 16)()
+        ok = L.hs_point_decode(enc, out)
+        p = o.point_from_bytes(enc)
+        assert bool(ok) == (p is not None)
+        if ok:
+            assert (val(out[:8]), val(out[8:])) == p
+
+
+def test_fixed_base_table_entries(L):
+    for which, w, j in [(0, 0, 1), (0, 0, 255), (0, 3, 17), (1, 31, 5), (1, 7, 200), (0, 31, 15), (1, 0, 0)]:
+        a, b = (C.c_uint32 * 24)(), (C.c_uint32 * 24)()
+        L.hs_fb_entry(which, w, j, a, b)
+        assert list(a) == list(b)
+
+
+def test_scalar_multiplications(L):
+    rnd = random.Random(6)
+    out = (C.c_uint8 * 32)()
+    for i in range(8):
+        k = rnd.randrange(o.R_ORDER) if i > 2 else [0, 1, o.R_ORDER - 1][i]
+        P = o.pmul(o.G, rnd.randrange(1, o.R_ORDER))
+        enc = o.point_to_bytes(P)
+        L.hs_varbase_mul(enc, o.le32(k), out, 0); assert bytes(out) == o.point_to_bytes(o.pmul(P, k))
+        L.hs_varbase_mul(enc, o.le32(k), out, 1); assert bytes(out) == o.point_to_bytes(o.pmul(o.G, k))
+        L.hs_varbase_mul(enc, o.le32(k), out, 2); assert bytes(out) == o.point_to_bytes(o.pmul(o.G_NUMS, k))
+
+
+def test_tate_subgroup_test_equals_definition(L):
+    rnd = random.Random(7)
+    t8 = adv.torsion()[8]
+    for _ in range(6):
+        cur = o.point_to_bytes(o.pmul(o.G, rnd.randrange(1, o.R_ORDER)))
+        for j in range(8):
+            assert L.hs_subgroup(cur, 0) == L.hs_subgroup(cur, 1) == (1 if j == 0 else 0)
+            cur = co.point_add(cur, t8)
+    cur = o.point_to_bytes(o.IDENTITY)
+    for j in range(8):
+        assert L.hs_subgroup(cur, 0) == L.hs_subgroup(cur, 1) == (1 if j == 0 else 0)
+        cur = co.point_add(cur, t8)
+    for _ in range(60):
+        enc = rnd.randbytes(32)
+        assert L.hs_subgroup(enc, 0) == L.hs_subgroup(enc, 1)
+
+
+def test_signing_twin_matches_oracle(L):
+    rnd = random.Random(8)
+    for variant in (0, 1, 2):
+        sk, rr, m, g = rnd.randrange(o.R_ORDER), rnd.randrange(o.R_ORDER), rnd.randrange(o.Q), rnd.randrange(1, o.R_ORDER)
+        pk, sig = (C.c_uint8 * 64)(), (C.c_uint8 * 96)()
+        assert L.hs_sign(variant, o.le32(sk), o.le32(rr), o.le32(g), o.le32(m), pk, sig)
+        if variant == 0:
+            u, R = o.sign_single(sk, rr, m)
+            epk, esig = o.point_to_bytes(o.pmul(o.G, sk)), o.le32(u) + o.point_to_bytes(R)
+        elif variant == 1:
+            u, R, Rp = o.sign_double(sk, rr, m)
+            epk = o.point_to_bytes(o.pmul(o.G, sk)) + o.point_to_bytes(o.pmul(o.G_NUMS, sk))
+            esig = o.le32(u) + o.point_to_bytes(R) + o.point_to_bytes(Rp)
+        else:
+            gen = o.pmul(o.G, g)
+            u, R = o.sign_var_gen(sk, gen, rr, m)
+            epk, esig = o.point_to_bytes(o.pmul(gen, sk)) + o.point_to_bytes(gen), o.le32(u) + o.point_to_bytes(R)
+        assert bytes(pk)[:len(epk)] == epk and bytes(sig)[:len(esig)] == esig
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
+def test_pipeline_twin_on_adversarial_batches(L, vi, kind):
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    n = 320
+    pk, sig, msg = gen(0xB200, n)
+    pk, sig, msg, exp, names = adv.make_adversarial(kind, pk, sig, msg, seed=7, frac=0.6)
+    st, c = ver(pk, sig, msg)
+    hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
+    L.hs_verify(vi, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
+    bad = np.nonzero(hst != st)[0]
+    assert bad.size == 0, [(int(i), names[i], int(hst[i]), int(st[i])) for i in bad[:5]]
+    assert np.array_equal(hc, c) and np.array_equal(st, exp)
+
+
+def test_aggregate_twin(L):
+    signers = [1, 2, 3, 4, 2, 3, 5, 2]
+    pks, off, sig, msg = co.gen_aggregate(11, signers)
+    sig[2, 0] ^= 1
+    pks[off[3]] = np.frombuffer(adv.torsion()[4], np.uint8)
+    pks[off[4]] = np.frombuffer(adv.off_curve_encoding(np.random.default_rng(1)), np.uint8)
+    st, c, agg = co.verify_aggregate(pks, off, sig, msg)
+    n = len(signers)
+    hst, hc, ha = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8), np.zeros((n, 32), np.uint8)
+    L.hs_verify_aggregate(_p(pks), _p(off), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc), _p(ha))
+    assert np.array_equal(hst, st) and np.array_equal(hc, c)
+    ok = st != 3
+    assert np.array_equal(ha[ok], agg[ok])
