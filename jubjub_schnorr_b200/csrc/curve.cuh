@@ -7,6 +7,7 @@
 #pragma once
 #include "consts.cuh"
 #include "fq.cuh"
+#include "scalar.cuh"
 
 namespace jjs {
 
@@ -57,7 +58,7 @@ JJS_HD void ext_from_affine(ext& p, const fq& u, const fq& v) {
 }
 // dbl-2008-hwcd with a = -1: 4S + 4M (3M when the T output is not needed)
 template <bool WANT_T>
-JJS_HD void ext_dbl(ext& r, const ext& p) {
+JJS_HD void ext_dbl_inl(ext& r, const ext& p) {
     fq a, b, c, e, f, g, h, t;
     fq_sqr(a, p.X);
     fq_sqr(b, p.Y);
@@ -78,7 +79,7 @@ JJS_HD void ext_dbl(ext& r, const ext& p) {
 }
 // add-2008-hwcd-3 (a = -1, complete since d is a non-square): extended + projective Niels, 8M (7M without T)
 template <bool WANT_T>
-JJS_HD void ext_add_pniels(ext& r, const ext& p, const pniels& q) {
+JJS_HD void ext_add_pniels_inl(ext& r, const ext& p, const pniels& q) {
     fq a, b, c, d, e, f, g, h, t;
     fq_sub(t, p.Y, p.X);
     fq_mul(a, t, q.ymx);
@@ -97,7 +98,7 @@ JJS_HD void ext_add_pniels(ext& r, const ext& p, const pniels& q) {
 }
 // extended + affine Niels (Z2 = 1): 7M (6M without T)
 template <bool WANT_T>
-JJS_HD void ext_add_niels(ext& r, const ext& p, const niels& q) {
+JJS_HD void ext_add_niels_inl(ext& r, const ext& p, const niels& q) {
     fq a, b, c, d, e, f, g, h, t;
     fq_sub(t, p.Y, p.X);
     fq_mul(a, t, q.ymx);
@@ -114,6 +115,45 @@ JJS_HD void ext_add_niels(ext& r, const ext& p, const niels& q) {
     fq_mul(r.Z, f, g);
     if (WANT_T) fq_mul(r.T, e, h);
 }
+// With -DJJS_POINT_CALLS (and -DJJS_INLINE_FIELD) the function-call boundary moves from the field multiplier up to
+// the point operations: one call per doubling / addition instead of 7-9 per point operation.
+#if defined(__CUDA_ARCH__) && defined(JJS_POINT_CALLS)
+template <bool WANT_T>
+__device__ __noinline__ ext ext_dbl_fn(ext p) {
+    ext r;
+    ext_dbl_inl<WANT_T>(r, p);
+    if (!WANT_T) r.T = p.T;
+    return r;
+}
+template <bool WANT_T>
+__device__ __noinline__ ext ext_add_pniels_fn(ext p, pniels q) {
+    ext r;
+    ext_add_pniels_inl<WANT_T>(r, p, q);
+    if (!WANT_T) r.T = p.T;
+    return r;
+}
+template <bool WANT_T>
+__device__ __noinline__ ext ext_add_niels_fn(ext p, niels q) {
+    ext r;
+    ext_add_niels_inl<WANT_T>(r, p, q);
+    if (!WANT_T) r.T = p.T;
+    return r;
+}
+template <bool WANT_T>
+JJS_HD void ext_dbl(ext& r, const ext& p) { r = ext_dbl_fn<WANT_T>(p); }
+template <bool WANT_T>
+JJS_HD void ext_add_pniels(ext& r, const ext& p, const pniels& q) { r = ext_add_pniels_fn<WANT_T>(p, q); }
+template <bool WANT_T>
+JJS_HD void ext_add_niels(ext& r, const ext& p, const niels& q) { r = ext_add_niels_fn<WANT_T>(p, q); }
+#else
+template <bool WANT_T>
+JJS_HD void ext_dbl(ext& r, const ext& p) { ext_dbl_inl<WANT_T>(r, p); }
+template <bool WANT_T>
+JJS_HD void ext_add_pniels(ext& r, const ext& p, const pniels& q) { ext_add_pniels_inl<WANT_T>(r, p, q); }
+template <bool WANT_T>
+JJS_HD void ext_add_niels(ext& r, const ext& p, const niels& q) { ext_add_niels_inl<WANT_T>(r, p, q); }
+#endif
+
 JJS_HD void ext_to_pniels(pniels& n, const ext& p) {
     fq d2;
     fq_load_const(d2, JJS_C(EDWARDS_2D));
@@ -391,6 +431,32 @@ JJS_HD void varbase_mul(ext& r, const fq* tab, size_t stride, const DIGITS& digi
 #pragma unroll 1
     for (int i = 62; i >= 1; i--) varbase_window<false>(acc, tab, stride, digits[i]);
     varbase_window<WANT_T>(acc, tab, stride, digits[0]);
+    r = acc;
+}
+
+// acc = sum_i 16^i (dA[i] * A + dB[i] * B) over N signed radix-16 digits each (Straus: the doublings are shared);
+// tabA / tabB are per-thread tables from varbase_table_build.  acc.T is defined on return.
+template <int N>
+JJS_HD void straus2(ext& r, const fq* tabA, const fq* tabB, size_t stride, const int8_t* dA, const int8_t* dB) {
+    ext acc, t;
+    pniels n;
+    ext_identity(acc);
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; i--) {
+        if (i != N - 1) {
+            ext_dbl<false>(t, acc);
+            ext_dbl<false>(acc, t);
+            ext_dbl<false>(t, acc);
+            ext_dbl<true>(acc, t);
+        }
+        int da = dA[i], db = dB[i];
+        pniels_load(n, tabA, stride, da < 0 ? -da : da);
+        pniels_cneg(n, da < 0);
+        ext_add_pniels<true>(t, acc, n);
+        pniels_load(n, tabB, stride, db < 0 ? -db : db);
+        pniels_cneg(n, db < 0);
+        ext_add_pniels<true>(acc, t, n);
+    }
     r = acc;
 }
 

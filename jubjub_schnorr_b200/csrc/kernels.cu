@@ -31,7 +31,7 @@ constexpr int BLOCK = 128;
 #define JJS_DEC_MINBLOCKS 4
 #endif
 constexpr size_t CHUNK_ITEMS = size_t(1) << 20;   // items per pipeline pass
-constexpr size_t TAB_THREADS = size_t(1) << 21;   // threads served by the per-thread table scratch (1152 B each)
+constexpr size_t TAB_THREADS = size_t(1) << 20;   // threads served by the per-thread table scratch (two tables of 1152 B each)
 
 struct Fields {
     WireField f[4];
@@ -90,11 +90,13 @@ __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int varian
     for (int s = 0; s < slots; s++) ready = ready && (pflags[s * n + item] & PF_DECODED);
     bool ok = false;
     if (ready) {
-        if (variant == VAR_SINGLE) ok = stage_equation(pts_u, pts_v, n, item, 0, 1, -1, T.fb_g, usc, cwords, tab + t, stride);
+        fq* tabA = tab + t;
+        fq* tabB = tab + 36 * stride + t;
+        if (variant == VAR_SINGLE) ok = stage_equation(pts_u, pts_v, n, item, 0, 1, -1, T.fb_g, usc, cwords, tabA, tabB, stride);
         else if (variant == VAR_DOUBLE)
-            ok = eq == 0 ? stage_equation(pts_u, pts_v, n, item, 0, 2, -1, T.fb_g, usc, cwords, tab + t, stride)
-                         : stage_equation(pts_u, pts_v, n, item, 1, 3, -1, T.fb_gn, usc, cwords, tab + t, stride);
-        else ok = stage_equation(pts_u, pts_v, n, item, 0, 2, 1, nullptr, usc, cwords, tab + t, stride);
+            ok = eq == 0 ? stage_equation(pts_u, pts_v, n, item, 0, 2, -1, T.fb_g, usc, cwords, tabA, tabB, stride)
+                         : stage_equation(pts_u, pts_v, n, item, 1, 3, -1, T.fb_gn, usc, cwords, tabA, tabB, stride);
+        else ok = stage_equation(pts_u, pts_v, n, item, 0, 2, 1, nullptr, usc, cwords, tabA, tabB, stride);
     }
     eqflags[g] = ok ? 1 : 0;
 }
@@ -242,7 +244,7 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaMalloc(&d.iflags, CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.eqflags, 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.cwords, 32 * CHUNK_ITEMS));
-    JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * 36 * TAB_THREADS));
+    JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * 2 * 36 * TAB_THREADS));
     return JJS_SUCCESS;
 }
 

@@ -1,0 +1,131 @@
+// Scalar-side helpers of the verify path: arithmetic modulo the subgroup order r (off the multiply-heavy path) and
+// the half-size decomposition of the challenge used by the equation kernel.
+#pragma once
+#include "consts.cuh"
+#include "fq.cuh"
+
+namespace jjs {
+
+// x (16 limbs, only the low `nbits` bits may be non-zero) mod r, bit-serial
+JJS_HD void fr_reduce_wide(uint32_t* out, const uint32_t* x16, int nbits = 512) {
+    uint32_t acc[8], ord[8], s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i] = 0; ord[i] = JJS_C(R_ORDER)[i]; }
+#pragma unroll 1
+    for (int bit = nbits - 1; bit >= 0; bit--) {
+        uint32_t in = (x16[bit >> 5] >> (bit & 31)) & 1u;
+#pragma unroll
+        for (int i = 7; i > 0; i--) acc[i] = (acc[i] << 1) | (acc[i - 1] >> 31);
+        acc[0] = (acc[0] << 1) | in;
+        uint32_t borrow = sub8(s, acc, ord);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = borrow ? acc[i] : s[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = acc[i];
+}
+JJS_HD void fr_mul(uint32_t* out, const uint32_t* a, const uint32_t* b, int nbits = 512) {
+    uint32_t t[16];
+    mul_wide(t, a, b);
+    fr_reduce_wide(out, t, nbits);
+}
+JJS_HD void fr_sub(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // a, b < r
+    uint32_t d[8], ord[8], e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ord[i] = JJS_C(R_ORDER)[i];
+    uint32_t borrow = sub8(d, a, b);
+    add8(e, d, ord);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = borrow ? e[i] : d[i];
+}
+
+JJS_HD double limbs_to_double(const uint32_t* a) {
+    double d = 0.0;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) d = d * 4294967296.0 + (double)a[i];
+    return d;
+}
+
+// Half-size decomposition of a challenge (Antipa, Brown, Gallant, Lambert, Struik, Vanstone: "Accelerated
+// verification of ECDSA signatures"): for c < r returns tau < 2^126 and rho != 0, |rho| < 2^126, with
+//     tau == rho * c  (mod r)            (rho = rho_neg ? -rho_abs : rho_abs)
+// by running the extended Euclidean algorithm on (r, c) until the remainder drops below 2^126.  Then, for points
+// of the prime-order subgroup,  u*G + c*PK == R   <=>   (rho*u)*G + tau*PK - rho*R == O,  which needs 126-bit
+// multipliers for the two variable bases.  Quotients are estimated from below in double precision (the margin
+// 2^-40 dwarfs the 2^-49 conversion error) and capped at 2^31 - 1; the exact comparison a >= b drives the loop, so
+// an underestimate only costs another pass.  Huge quotients are consumed 32 bits at a time.
+JJS_HD void half_gcd(uint32_t* tau4, uint32_t* rho4, bool& rho_neg, const uint32_t* c8) {
+    uint32_t a[8], b[8], ta[4] = {0, 0, 0, 0}, tb[4] = {1, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = JJS_C(R_ORDER)[i]; b[i] = c8[i]; }
+    bool neg = false;
+#pragma unroll 1
+    while ((b[7] | b[6] | b[5] | b[4]) != 0u || b[3] >= (1u << 30)) {
+        uint32_t tmp[8];
+#pragma unroll 1
+        while (sub8(tmp, a, b) == 0u) {  // a >= b
+            double qd = limbs_to_double(a) / limbs_to_double(b) * (1.0 - 9.094947017729282e-13);
+            // quotients of 2^32 and more (probability 2^-32 per step for a hash output, but they must not stall the
+            // loop) are taken one 32-bit digit at a time: q * 2^(32 k) <= a / b, applied to limb-shifted copies
+            uint32_t bs[8], ts[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) bs[i] = b[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) ts[i] = tb[i];
+#pragma unroll 1
+            while (qd >= 4294967296.0) {
+                qd *= 2.3283064365386963e-10;
+#pragma unroll
+                for (int i = 7; i > 0; i--) bs[i] = bs[i - 1];
+                bs[0] = 0;
+#pragma unroll
+                for (int i = 3; i > 0; i--) ts[i] = ts[i - 1];
+                ts[0] = 0;
+            }
+            uint32_t q = (uint32_t)qd;
+            if (q == 0u) q = 1u;
+            uint64_t carry = 0;
+            int64_t borrow = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {  // a -= q * bs
+                uint64_t p = (uint64_t)q * bs[i] + carry;
+                carry = p >> 32;
+                int64_t dlt = (int64_t)a[i] - (int64_t)(uint32_t)p + borrow;
+                a[i] = (uint32_t)dlt;
+                borrow = dlt >> 32;
+            }
+            carry = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {  // ta += q * ts   (stays below 2^126)
+                uint64_t p = (uint64_t)q * ts[i] + ta[i] + carry;
+                ta[i] = (uint32_t)p;
+                carry = p >> 32;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { uint32_t x = a[i]; a[i] = b[i]; b[i] = x; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { uint32_t x = ta[i]; ta[i] = tb[i]; tb[i] = x; }
+        neg = !neg;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { tau4[i] = b[i]; rho4[i] = tb[i]; }
+    rho_neg = neg;
+}
+
+// signed radix-16 digits d_i in [-8, 8) of a little-endian scalar of NLIMBS limbs; writes 8 * NLIMBS + 1 digits
+// (the last one is the final carry, 0 or 1).  For scalars below 2^(32 NLIMBS - 3) the last digit is 0.
+template <int NLIMBS>
+JJS_HD void recode_signed16_n(int8_t* digits, const uint32_t* k, bool negate) {
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < 8 * NLIMBS; i++) {
+        int d = (int)((k[i >> 3] >> ((i & 7) * 4)) & 15u) + (int)carry;
+        carry = d >= 8;
+        d -= (int)(carry << 4);
+        digits[i] = (int8_t)(negate ? -d : d);
+    }
+    digits[8 * NLIMBS] = (int8_t)(negate ? -(int)carry : (int)carry);
+}
+
+}  // namespace jjs

@@ -11,38 +11,6 @@
 
 namespace jjs {
 
-// x (16 limbs) mod r, bit-serial (off the hot path)
-JJS_HD void fr_reduce_wide(uint32_t* out, const uint32_t* x16) {
-    uint32_t acc[8], ord[8], s[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { acc[i] = 0; ord[i] = JJS_C(R_ORDER)[i]; }
-#pragma unroll 1
-    for (int bit = 511; bit >= 0; bit--) {
-        uint32_t in = (x16[bit >> 5] >> (bit & 31)) & 1u;
-#pragma unroll
-        for (int i = 7; i > 0; i--) acc[i] = (acc[i] << 1) | (acc[i - 1] >> 31);
-        acc[0] = (acc[0] << 1) | in;
-        uint32_t borrow = sub8(s, acc, ord);
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = borrow ? acc[i] : s[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = acc[i];
-}
-JJS_HD void fr_mul(uint32_t* out, const uint32_t* a, const uint32_t* b) {
-    uint32_t t[16];
-    mul_wide(t, a, b);
-    fr_reduce_wide(out, t);
-}
-JJS_HD void fr_sub(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // a, b < r
-    uint32_t d[8], ord[8], e[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) ord[i] = JJS_C(R_ORDER)[i];
-    uint32_t borrow = sub8(d, a, b);
-    add8(e, d, ord);
-#pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = borrow ? e[i] : d[i];
-}
 JJS_HD void ext_to_affine(fq& u, fq& v, const ext& p) {
     fq zi;
     fq_inv(zi, p.Z);

@@ -131,32 +131,48 @@ JJS_HD uint8_t subgroup_check(const WireField& f, size_t i, int method, fq* tab,
 }
 
 // ---- stage 4: one verification equation  u*B + c*PK == R ------------------------------------------
-// base_slot < 0: fixed base table `fb`; otherwise the decoded point in that slot is the base (var-gen).
+// Two per-thread tables (tabA, tabB).  Fixed base (base_slot < 0, table `fb`): the challenge is split as
+// tau == rho * c (mod r) with 126-bit tau, rho (half_gcd), and the equivalent check
+//     (|rho| u mod r) * B  +  sign(rho) tau * PK  -  |rho| * R  ==  O
+// is evaluated with 33 shared-doubling windows instead of 64.  The equivalence needs PK and R in the prime-order
+// subgroup (rho is invertible mod r): callers only use the result when every point passed is_valid(), which is
+// exactly when the reference evaluates the equation.  Variable base (var-gen): u*Gen + c*PK by a 64-window Straus
+// interleave, compared projectively with R.
 JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t item, int pk_slot, int r_slot, int base_slot,
-                           const niels* fb, const WireField& usc, const uint32_t* c_words, fq* tab, size_t stride) {
+                           const niels* fb, const WireField& usc, const uint32_t* c_words, fq* tabA, fq* tabB, size_t stride) {
     uint32_t u[8], c[8];
     wire_load(u, usc, item);
 #pragma unroll
     for (int i = 0; i < 8; i++) c[i] = c_words[item * 8 + i];
-    int8_t digits[64];
-    ext acc, ub;
-    // c * PK
-    varbase_table_build(tab, stride, pts_u[pk_slot * n + item], pts_v[pk_slot * n + item]);
-    recode_signed16(digits, c);
-    varbase_mul<true>(acc, tab, stride, digits);
-    // u * B
+    ext acc;
     if (base_slot < 0) {
-        fixedbase_mul(ub, fb, u);
-    } else {
-        varbase_table_build(tab, stride, pts_u[base_slot * n + item], pts_v[base_slot * n + item]);
-        recode_signed16(digits, u);
-        varbase_mul<true>(ub, tab, stride, digits);
+        uint32_t tau[4], rho[8];
+        bool rho_neg;
+        half_gcd(tau, rho, rho_neg, c);
+#pragma unroll
+        for (int i = 4; i < 8; i++) rho[i] = 0;
+        int8_t dT[33], dR[33];
+        recode_signed16_n<4>(dT, tau, rho_neg);
+        recode_signed16_n<4>(dR, rho, true);
+        varbase_table_build(tabA, stride, pts_u[pk_slot * n + item], pts_v[pk_slot * n + item]);
+        varbase_table_build(tabB, stride, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
+        straus2<33>(acc, tabA, tabB, stride, dT, dR);
+        uint32_t ru[8];
+        fr_mul(ru, rho, u, 384);  // |rho| * u < 2^126 * 2^252
+        ext ub, sum;
+        fixedbase_mul(ub, fb, ru);
+        pniels nb;
+        ext_to_pniels(nb, ub);
+        ext_add_pniels<false>(sum, acc, nb);
+        return ext_is_identity(sum);
     }
-    pniels nb;
-    ext_to_pniels(nb, ub);
-    ext sum;
-    ext_add_pniels<false>(sum, acc, nb);
-    return ext_eq_affine(sum, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
+    int8_t dU[64], dC[64];
+    recode_signed16(dU, u);
+    recode_signed16(dC, c);
+    varbase_table_build(tabA, stride, pts_u[base_slot * n + item], pts_v[base_slot * n + item]);
+    varbase_table_build(tabB, stride, pts_u[pk_slot * n + item], pts_v[pk_slot * n + item]);
+    straus2<64>(acc, tabA, tabB, stride, dU, dC);
+    return ext_eq_affine(acc, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
 }
 
 // ---- aggregate key: multisig::aggregate_pk (reference src/multisig.rs:154-156, 393-429) ---------------

@@ -138,7 +138,7 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
                          uint8_t* c_out, uint8_t* agg_out) {
     ensure_ready();
     size_t K = offsets[n];
-    std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(36);
+    std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(72);
     std::vector<uint8_t> kf(K), pf(2 * n), itf(n);
     std::vector<uint32_t> cw(8 * n);
     WireField fk{pks, 32}, fR{sig + 32, 64}, fmsg{msg, 32}, fu{sig, 64};
@@ -150,10 +150,20 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
         stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables);
         stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
         bool all = (itf[i] & IF_SCALARS_OK) && (pf[i] & PF_DECODED) && (pf[n + i] & PF_DECODED);
-        if (all && stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
+        if (all && stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
         status[i] = stage_status(VAR_SINGLE, pf.data(), itf[i], n, i);
         if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
     }
+}
+// half-size decomposition: outputs tau (16 bytes), |rho| (16 bytes), returns sign of rho (1 = negative)
+int hs_half_gcd(const uint8_t* c32, uint8_t* tau16, uint8_t* rho16) {
+    uint32_t c[8], tau[4], rho[4];
+    memcpy(c, c32, 32);
+    bool neg;
+    half_gcd(tau, rho, neg, c);
+    memcpy(tau16, tau, 16);
+    memcpy(rho16, rho, 16);
+    return neg;
 }
 int hs_subgroup(const uint8_t* p32, int method) {
     ensure_ready();
@@ -180,7 +190,7 @@ void hs_verify(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t
     else if (variant == VAR_DOUBLE) { f[0] = {pk, 64}; f[1] = {pk + 32, 64}; f[2] = {sig + 32, 96}; f[3] = {sig + 64, 96}; }
     else { f[0] = {pk, 64}; f[1] = {pk + 32, 64}; f[2] = {sig + 32, 64}; }
     (void)pk_stride;
-    std::vector<fq> pu(slots * n), pv(slots * n), tab(36);
+    std::vector<fq> pu(slots * n), pv(slots * n), tab(72);
     std::vector<uint8_t> pf(slots * n), itf(n);
     std::vector<uint32_t> cw(8 * n);
     for (int s = 0; s < slots; s++)
@@ -191,12 +201,12 @@ void hs_verify(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t
         for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);
         if (all) {
             if (variant == VAR_SINGLE) {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
             } else if (variant == VAR_DOUBLE) {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, -1, g_tables.fb_g, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
-                if (stage_equation(pu.data(), pv.data(), n, i, 1, 3, -1, g_tables.fb_gn, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ1_OK;
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
+                if (stage_equation(pu.data(), pv.data(), n, i, 1, 3, -1, g_tables.fb_gn, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ1_OK;
             } else {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, 1, nullptr, fu, cw.data(), tab.data(), 1)) itf[i] |= IF_EQ0_OK;
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, 1, nullptr, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
             }
         }
         status[i] = stage_status(variant, pf.data(), itf[i], n, i);
