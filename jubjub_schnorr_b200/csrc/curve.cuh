@@ -19,7 +19,10 @@ JJS_HD void fq_load_const(fq& r, const uint32_t* c) {
 // ---------------------------------------------------------------------------------------------
 // large lookup tables living in global memory (device) or in the generated host arrays (hostsim)
 // ---------------------------------------------------------------------------------------------
-constexpr int FB_W = 8;                       // fixed-base window width (bits)
+#ifndef JJS_FB_W
+#define JJS_FB_W 12
+#endif
+constexpr int FB_W = JJS_FB_W;                // fixed-base window width (bits): 21 windows x 4096 entries x 96 B = 8.3 MB per base, L2 resident
 constexpr int FB_WINDOWS = (252 + FB_W - 1) / FB_W;
 constexpr int FB_ENTRIES = 1 << FB_W;
 

@@ -21,30 +21,45 @@ static void build_fb(std::vector<niels>& out, const uint32_t uv[2][8]) {
     memcpy(u.l, uv[0], 32);
     memcpy(v.l, uv[1], 32);
     out.resize((size_t)FB_WINDOWS * FB_ENTRIES);
-    // incremental construction (fb_table_entry itself is exercised by hs_fb_entry)
+    // incremental construction with one batched inversion per window (fb_table_entry itself is exercised by hs_fb_entry)
     ext base;
     ext_from_affine(base, u, v);
+    std::vector<ext> pts(FB_ENTRIES);
+    std::vector<fq> prefix(FB_ENTRIES);
+    fq d2;
+    fq_load_const(d2, JJS_C(EDWARDS_2D));
     for (int w = 0; w < FB_WINDOWS; w++) {
         pniels nb;
         ext_to_pniels(nb, base);
         ext acc;
         ext_identity(acc);
         for (int j = 0; j < FB_ENTRIES; j++) {
-            fq zi, au, av, d2;
-            fq_inv(zi, acc.Z);
-            fq_mul(au, acc.X, zi);
-            fq_mul(av, acc.Y, zi);
-            fq_load_const(d2, JJS_C(EDWARDS_2D));
-            niels& e = out[(size_t)w * FB_ENTRIES + j];
-            fq_add(e.ypx, av, au);
-            fq_sub(e.ymx, av, au);
-            fq_mul(e.t2d, au, av);
-            fq_mul(e.t2d, e.t2d, d2);
+            pts[j] = acc;
             ext t;
             ext_add_pniels<true>(t, acc, nb);
             acc = t;
         }
         base = acc;  // 2^FB_W * previous base
+        fq run;
+        fq_one(run);
+        for (int j = 0; j < FB_ENTRIES; j++) {
+            prefix[j] = run;
+            fq_mul(run, run, pts[j].Z);
+        }
+        fq inv_all;
+        fq_inv(inv_all, run);
+        for (int j = FB_ENTRIES - 1; j >= 0; j--) {
+            fq zi, au, av;
+            fq_mul(zi, inv_all, prefix[j]);
+            fq_mul(inv_all, inv_all, pts[j].Z);
+            fq_mul(au, pts[j].X, zi);
+            fq_mul(av, pts[j].Y, zi);
+            niels& e = out[(size_t)w * FB_ENTRIES + j];
+            fq_add(e.ypx, av, au);
+            fq_sub(e.ymx, av, au);
+            fq_mul(e.t2d, au, av);
+            fq_mul(e.t2d, e.t2d, d2);
+        }
     }
 }
 

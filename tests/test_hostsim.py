@@ -110,7 +110,7 @@ def test_point_decode(L):
 
 
 def test_fixed_base_table_entries(L):
-    for which, w, j in [(0, 0, 1), (0, 0, 255), (0, 3, 17), (1, 31, 5), (1, 7, 200), (0, 31, 15), (1, 0, 0)]:
+    for which, w, j in [(0, 0, 1), (0, 0, 255), (0, 3, 17), (1, 20, 5), (1, 7, 200), (0, 20, 4095), (1, 0, 0), (0, 11, 2049)]:
         a, b = (C.c_uint32 * 24)(), (C.c_uint32 * 24)()
         L.hs_fb_entry(which, w, j, a, b)
         assert list(a) == list(b)
