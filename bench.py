@@ -165,7 +165,19 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to stdout while the communicator is created; stdout must carry one JSON
+        # line only, so fd 1 points at stderr until the first collective is through.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     # single-process launch with --gpus N > 1: one context over N devices (the library shards internally)
     devices = [local_rank] if world > 1 else list(range(args.gpus))
     n_local = (1 << args.log2n) * (1 if world > 1 else args.gpus)
