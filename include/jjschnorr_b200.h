@@ -91,6 +91,12 @@ int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk
                              const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
                              void* cuda_stream);
 
+/* Aggregate-key verification on device buffers.  d_offsets / h_offsets: the same n + 1 offsets on the device and on
+ * the host (the host copy plans the 2^20-item chunks). */
+int jjs_verify_aggregate_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pks32, const uint32_t* d_offsets,
+                                const uint32_t* h_offsets, const uint8_t* d_sig64, const uint8_t* d_msg32, size_t n,
+                                uint8_t* d_status, uint8_t* d_c32_or_null, uint8_t* d_aggpk32_or_null, void* cuda_stream);
+
 /* Challenge hash only (hash parity hook): c = challenge_hash(..) for already-valid encodings, no curve
  * check.  variant: 0 single, 1 double, 2 var-generator.  Host buffers. */
 int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32,
@@ -113,8 +119,15 @@ int jjs_sign_batch(jjs_ctx* ctx, int variant, const uint8_t* sk32, const uint8_t
                    const uint8_t* gen_scalar32_or_null, const uint8_t* msg32, size_t n, uint8_t* pk_out,
                    uint8_t* sig_out);
 
+/* Synthetic aggregate-key items: signer keys pk_j = sk_j * G (written to pks32_out, ragged like sk32 / offsets, at most 8
+ * signers per item), and a hedged Schnorr signature under the aggregate secret sum_j d_j sk_j with the reference's
+ * delinearisation coefficients (src/multisig.rs:393-409) -- i.e. what jjs_verify_aggregate accepts.  Host buffers. */
+int jjs_sign_aggregate_batch(jjs_ctx* ctx, const uint8_t* sk32, const uint32_t* offsets, const uint8_t* rnd32,
+                             const uint8_t* msg32, size_t n, uint8_t* pks32_out, uint8_t* sig64_out);
+
 /* Per-stage device timing (CUDA events on the launching stream around each pipeline stage):
- * stage 0 point decode + subgroup test, 1 challenge hash, 2 (unused), 3 verification equations, 4 status.
+ * stage 0 point decode + subgroup test, 1 challenge hash, 2 key aggregation (aggregate path only), 3 verification
+ * equations, 4 status.
  * jjs_profile_collect waits for the recorded events, adds their durations (ms) and occurrence counts per
  * stage into the two JJS_N_STAGES-long arrays, and clears the records. */
 #define JJS_N_STAGES 5

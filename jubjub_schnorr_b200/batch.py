@@ -67,7 +67,7 @@ class BatchVerifier:
     def launch_count(self) -> int:
         return int(self._lib.jjs_launch_count(self._ctx))
 
-    STAGES = ("decode", "challenge", "subgroup", "equation", "status")
+    STAGES = ("decode", "challenge", "aggregate", "equation", "status")
 
     def profile(self, on: bool):
         self._lib.jjs_profile_enable(self._ctx, int(on))
@@ -146,6 +146,24 @@ class BatchVerifier:
         self._check(self._lib.jjs_sign_batch(self._ctx, variant, sk.ctypes.data, rnd.ctypes.data, gsc.ctypes.data if gsc is not None else None,
                                              msg.ctypes.data, n, pk.ctypes.data, sig.ctypes.data), "jjs_sign_batch")
         return pk, sig
+
+    def sign_aggregate_batch(self, sk32, offsets, rnd32, msg32):
+        """(signer keys [K,32], signatures [n,64]) for ragged signer sets; see jjs_sign_aggregate_batch."""
+        sk, rnd, msg = _u8(sk32, 32, "sk"), _u8(rnd32, 32, "rnd"), _u8(msg32, 32, "msg")
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = msg.shape[0]
+        if offsets.shape[0] != n + 1 or int(offsets[-1]) != sk.shape[0] or int(offsets[0]) != 0:
+            raise ValueError("offsets must have n + 1 entries covering sk32 exactly")
+        pks = np.empty((sk.shape[0], 32), dtype=np.uint8)
+        sig = np.empty((n, 64), dtype=np.uint8)
+        self._check(self._lib.jjs_sign_aggregate_batch(self._ctx, sk.ctypes.data, offsets.ctypes.data, rnd.ctypes.data, msg.ctypes.data, n,
+                                                       pks.ctypes.data, sig.ctypes.data), "jjs_sign_aggregate_batch")
+        return pks, sig
+
+    def verify_aggregate_device(self, d_pks, d_offsets, h_offsets, d_sig, d_msg, n, d_status, d_c=None, d_agg=None, stream=None, device_index=0):
+        h_offsets = np.ascontiguousarray(h_offsets, dtype=np.uint32)
+        self._check(self._lib.jjs_verify_aggregate_device(self._ctx, device_index, d_pks, d_offsets, h_offsets.ctypes.data, d_sig, d_msg, n,
+                                                          d_status, d_c, d_agg, stream), "jjs_verify_aggregate_device")
 
     # ---- raw host / device pointers (pinned torch tensors, device tensors: pass .data_ptr()) ----------
     def verify_host_ptr(self, variant, pk_ptr, sig_ptr, msg_ptr, n, status_ptr, c_ptr=None):

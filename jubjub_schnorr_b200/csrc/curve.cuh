@@ -59,7 +59,10 @@ JJS_HD void ext_from_affine(ext& p, const fq& u, const fq& v) {
     fq_one(p.Z);
     fq_mul(p.T, u, v);
 }
-// dbl-2008-hwcd with a = -1: 4S + 4M (3M when the T output is not needed)
+// dbl-2008-hwcd with a = -1: 4S + 4M (3M when the T output is not needed).  With D = -A the formulas
+//   E = (X+Y)^2 - A - B, G = D + B, F = G - C, H = D - B,  X3 = E F, Y3 = G H, T3 = E H, Z3 = F G
+// are evaluated on the negated quantities E' = A + B - (X+Y)^2, G' = A - B, F' = G' + C, H' = A + B, for which all four
+// products keep their sign (E'F' = EF, G'H' = GH, E'H' = EH, F'G' = FG): six additions instead of eight, no negation.
 template <bool WANT_T>
 JJS_HD void ext_dbl_inl(ext& r, const ext& p) {
     fq a, b, c, e, f, g, h, t;
@@ -69,12 +72,10 @@ JJS_HD void ext_dbl_inl(ext& r, const ext& p) {
     fq_dbl(c, c);
     fq_add(t, p.X, p.Y);
     fq_sqr(e, t);
-    fq_sub(e, e, a);
-    fq_sub(e, e, b);   // E = 2XY
-    fq_sub(g, b, a);   // G = D + B, D = -A
-    fq_sub(f, g, c);   // F = G - C
-    fq_add(h, a, b);
-    fq_neg(h, h);      // H = D - B = -(A + B)
+    fq_add(h, a, b);   // H'
+    fq_sub(e, h, e);   // E'
+    fq_sub(g, a, b);   // G'
+    fq_add(f, g, c);   // F'
     fq_mul(r.X, e, f);
     fq_mul(r.Y, g, h);
     fq_mul(r.Z, f, g);

@@ -135,8 +135,35 @@ JJS_HD void mad_diag8(uint32_t* t, const uint32_t* a) {
 #endif
 }
 
-// r[0..7] = x[0..7] + y[0..7] + cin (cin in {0,1}); returns carry out in {0,1}.
-JJS_HD uint32_t add8(uint32_t* r, const uint32_t* x, const uint32_t* y, uint32_t cin = 0) {
+// r[0..7] = x[0..7] + y[0..7]; returns carry out in {0,1}.
+JJS_HD uint32_t add8(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+    uint32_t cout;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(cout)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y[0]), "r"(y[1]),
+          "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]));
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)x[i] + y[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    cout = (uint32_t)c;
+#endif
+    return cout;
+}
+// same with a carry in (cin in {0,1})
+JJS_HD uint32_t add8c(uint32_t* r, const uint32_t* x, const uint32_t* y, uint32_t cin) {
     uint32_t cout;
 #if defined(__CUDA_ARCH__)
     asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"  // CF = cin
@@ -348,7 +375,7 @@ JJS_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
     uint32_t x[8] = {E[9], E[10], E[11], E[12], E[13], E[14], E[15], 0};
     uint32_t y[8] = {O[8], O[9], O[10], O[11], O[12], O[13], O[14], 0};
     uint32_t hi[8];
-    add8(hi, x, y, c);
+    add8c(hi, x, y, c);
 #pragma unroll
     for (int i = 0; i < 7; i++) t[9 + i] = hi[i];
 }
@@ -380,7 +407,7 @@ JJS_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
     uint32_t x[8] = {E[9], E[10], E[11], E[12], E[13], E[14], 0, 0};
     uint32_t y[8] = {O[8], O[9], O[10], O[11], O[12], O[13], O[14], 0};
     uint32_t hi[8];
-    add8(hi, x, y, c);
+    add8c(hi, x, y, c);
 #pragma unroll
     for (int i = 0; i < 7; i++) s[9 + i] = hi[i];
     // t = 2 s + diagonal

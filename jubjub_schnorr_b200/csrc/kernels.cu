@@ -156,6 +156,65 @@ __global__ void __launch_bounds__(BLOCK) k_sign(const uint8_t* sk, const uint8_t
     for (int k = 0; k < SGW / 4; k++) so[k] = ok ? make_uint4(sig[4 * k], sig[4 * k + 1], sig[4 * k + 2], sig[4 * k + 3]) : make_uint4(0, 0, 0, 0);
 }
 
+// Aggregate-key items for synthetic batches: signer keys pk_j = sk_j * G, the aggregate secret sum_j d_j sk_j with the
+// reference's delinearisation coefficients, and an ordinary hedged signature under it (what a completed SpeedyMuSig
+// session verifies as).  At most JJS_MAX_GEN_SIGNERS signers per item.
+#define JJS_MAX_GEN_SIGNERS 8
+__global__ void __launch_bounds__(BLOCK) k_sign_aggregate(const uint8_t* sk, const uint32_t* offsets, const uint8_t* rnd, const uint8_t* msg, size_t n,
+                                                          uint8_t* pks_out, uint8_t* sig_out, Tables T) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t lo = offsets[i], hi = offsets[i + 1];
+    uint32_t cnt = hi - lo;
+    fq ku[JJS_MAX_GEN_SIGNERS], kv[JJS_MAX_GEN_SIGNERS];
+    uint32_t agg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ord[8], w[8];
+    bool ok = cnt <= JJS_MAX_GEN_SIGNERS;
+#pragma unroll
+    for (int k = 0; k < 8; k++) ord[k] = JJS_C(R_ORDER)[k];
+    if (ok) {
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j++) {
+            wire_load(w, WireField{sk, 32}, lo + j);
+            ok = ok && fr_wire_is_canonical(w);
+            ext P;
+            fixedbase_mul(P, T.fb_g, w);
+            ext_to_affine(ku[j], kv[j], P);
+            uint32_t enc[8];
+            point_to_wire(enc, ku[j], kv[j]);
+            uint4* o = reinterpret_cast<uint4*>(pks_out + 32 * (size_t)(lo + j));
+            o[0] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
+            o[1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
+        }
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j++) {
+            Sponge sp;
+            sponge_start(sp, (int)(2 + 2 * cnt));
+            sponge_absorb(sp, ku[j]);
+            sponge_absorb(sp, kv[j]);
+#pragma unroll 1
+            for (uint32_t k = 0; k < cnt; k++) {
+                sponge_absorb(sp, ku[k]);
+                sponge_absorb(sp, kv[k]);
+            }
+            uint32_t dj[8], t[8], s[8];
+            sponge_squeeze_truncated(dj, sp);
+            wire_load(w, WireField{sk, 32}, lo + j);
+            fr_mul(t, dj, w);
+            add8(s, agg, t);  // < 2r < 2^256
+            uint32_t borrow = sub8(t, s, ord);
+#pragma unroll
+            for (int k = 0; k < 8; k++) agg[k] = borrow ? s[k] : t[k];
+        }
+    }
+    uint32_t wr[8], wm[8], pk[16], sig[24];
+    wire_load(wr, WireField{rnd, 32}, i);
+    wire_load(wm, WireField{msg, 32}, i);
+    ok = ok && sign_item(VAR_SINGLE, agg, wr, wr, wm, pk, sig, T);
+    uint4* so = reinterpret_cast<uint4*>(sig_out + 64 * i);
+#pragma unroll
+    for (int k = 0; k < 4; k++) so[k] = ok ? make_uint4(sig[4 * k], sig[4 * k + 1], sig[4 * k + 2], sig[4 * k + 3]) : make_uint4(0, 0, 0, 0);
+}
+
 struct DeviceState {
     int device = -1;
     cudaStream_t stream = nullptr;
@@ -169,8 +228,7 @@ struct DeviceState {
     uint32_t* cwords = nullptr;
     // decoded signer keys of the aggregate-key path (grown on demand)
     fq *keys_u = nullptr, *keys_v = nullptr;
-    uint8_t *kflags = nullptr, *s_keys = nullptr, *s_agg = nullptr;
-    uint32_t* s_offsets = nullptr;
+    uint8_t* kflags = nullptr;
     size_t cap_keys = 0;
     // staging for the host-buffer entry points
     uint8_t *s_pk = nullptr, *s_sig = nullptr, *s_msg = nullptr, *s_status = nullptr, *s_c = nullptr;
@@ -364,64 +422,59 @@ int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, c
     return JJS_SUCCESS;
 }
 
-// aggregate_pk(..).verify(..) for a contiguous range of items on one device (host buffers; joined by the caller)
-int run_aggregate_shard(jjs_ctx* ctx, DeviceState& d, const uint8_t* pks, const uint32_t* offsets, const uint8_t* sig, const uint8_t* msg, size_t n,
-                        uint8_t* status, uint8_t* c_out, uint8_t* agg_out) {
+// aggregate_pk(..).verify(..) for n items whose wire data already sits on the device.  `h_offsets` is the host copy of
+// the n + 1 offsets (needed to plan the chunks); d_offsets the same array on the device.
+int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, const uint32_t* d_offsets, const uint32_t* h_offsets,
+                         const uint8_t* d_sig, const uint8_t* d_msg, size_t n, uint8_t* d_status, uint8_t* d_c, uint8_t* d_agg,
+                         cudaStream_t stream) {
     int rc = ensure_scratch(ctx, d);
-    if (rc) return rc;
-    rc = ensure_staging(ctx, d, n < CHUNK_ITEMS ? n : CHUNK_ITEMS);
     if (rc) return rc;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
     Tables T = d.tables();
-    cudaStream_t stream = d.stream;
     for (size_t off = 0; off < n; off += CHUNK_ITEMS) {
         size_t m = n - off < CHUNK_ITEMS ? n - off : CHUNK_ITEMS;
-        uint32_t key_lo = offsets[off], key_hi = offsets[off + m];
+        uint32_t key_lo = h_offsets[off], key_hi = h_offsets[off + m];
         size_t K = key_hi - key_lo;
         if (K > d.cap_keys) {
             JJS_CUDA(ctx, cudaStreamSynchronize(stream));
-            cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.s_keys);
-            d.keys_u = d.keys_v = nullptr; d.kflags = d.s_keys = nullptr; d.cap_keys = 0;
+            cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags);
+            d.keys_u = d.keys_v = nullptr; d.kflags = nullptr; d.cap_keys = 0;
             JJS_CUDA(ctx, cudaMalloc(&d.keys_u, sizeof(fq) * K));
             JJS_CUDA(ctx, cudaMalloc(&d.keys_v, sizeof(fq) * K));
             JJS_CUDA(ctx, cudaMalloc(&d.kflags, K));
-            JJS_CUDA(ctx, cudaMalloc(&d.s_keys, 32 * K));
             d.cap_keys = K;
         }
-        if (!d.s_offsets) {
-            JJS_CUDA(ctx, cudaMalloc(&d.s_offsets, sizeof(uint32_t) * (CHUNK_ITEMS + 1)));
-            JJS_CUDA(ctx, cudaMalloc(&d.s_agg, 32 * CHUNK_ITEMS));
-        }
-        if (K) JJS_CUDA(ctx, cudaMemcpyAsync(d.s_keys, pks + 32 * (size_t)key_lo, 32 * K, cudaMemcpyHostToDevice, stream));
-        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_offsets, offsets + off, sizeof(uint32_t) * (m + 1), cudaMemcpyHostToDevice, stream));
-        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_sig, sig + 64 * off, 64 * m, cudaMemcpyHostToDevice, stream));
-        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, stream));
         Fields fk, fr;
-        fk.f[0] = WireField{d.s_keys, 32};
-        fr.f[0] = WireField{d.s_sig + 32, 64};
+        fk.f[0] = WireField{d_pks + 32 * (size_t)key_lo, 32};
+        fr.f[0] = WireField{d_sig + 64 * off + 32, 64};
         fk.f[1] = fk.f[2] = fk.f[3] = fr.f[1] = fr.f[2] = fr.f[3] = WireField{nullptr, 0};
-        WireField fmsg{d.s_msg, 32}, fu{d.s_sig, 64};
+        WireField fmsg{d_msg + 32 * off, 32}, fu{d_sig + 64 * off, 64};
+        StageTimer t0(ctx, d.device, 0, stream);
         if (K) k_decode<<<blocks_for(K), BLOCK, 0, stream>>>(fk, 1, 0, K, d.keys_u, d.keys_v, d.kflags, T, false);
-        for (size_t first = 0; first < m; first += TAB_THREADS) {  // m <= CHUNK_ITEMS <= TAB_THREADS: one launch
-            size_t cnt = m - first < TAB_THREADS ? m - first : TAB_THREADS;
-            k_aggregate<<<blocks_for(cnt), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d.s_offsets, key_lo, m, d.pts_u, d.pts_v, d.pflags,
-                                                              agg_out ? d.s_agg : nullptr, d.tab, TAB_THREADS);
-        }
         k_decode<<<blocks_for(m), BLOCK, 0, stream>>>(fr, 1, 1, m, d.pts_u, d.pts_v, d.pflags, T, true);
+        t0.stop(stream);
+        StageTimer t2(ctx, d.device, 2, stream);
+        k_aggregate<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, key_lo, m, d.pts_u, d.pts_v, d.pflags,
+                                                        d_agg ? d_agg + 32 * off : nullptr, d.tab, TAB_THREADS);
+        t2.stop(stream);
+        StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
+        t1.stop(stream);
+        StageTimer t3(ctx, d.device, 3, stream);
         k_equation<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, d.iflags, m, 0, m, fu, d.cwords, d.eqflags, d.tab,
                                                        TAB_THREADS, T);
-        k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d.s_status, c_out ? d.s_c : nullptr);
+        t3.stop(stream);
+        StageTimer t4(ctx, d.device, 4, stream);
+        k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d_status + off,
+                                                       d_c ? d_c + 32 * off : nullptr);
+        t4.stop(stream);
         ctx->launches += 6;
-        JJS_CUDA(ctx, cudaGetLastError());
-        JJS_CUDA(ctx, cudaMemcpyAsync(status + off, d.s_status, m, cudaMemcpyDeviceToHost, stream));
-        if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + 32 * off, d.s_c, 32 * m, cudaMemcpyDeviceToHost, stream));
-        if (agg_out) JJS_CUDA(ctx, cudaMemcpyAsync(agg_out + 32 * off, d.s_agg, 32 * m, cudaMemcpyDeviceToHost, stream));
-        if (off + m < n) JJS_CUDA(ctx, cudaStreamSynchronize(stream));  // staging buffers are reused by the next chunk
     }
+    JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
 }
 
+// host buffers: contiguous shards over the devices, each shard copied to temporary device buffers
 int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status,
                   uint8_t* c_out, uint8_t* agg_out) {
     if (!ctx) return JJS_ERR_ARGUMENT;
@@ -433,17 +486,37 @@ int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, con
     if (offsets[n] > offsets[0] && !pks) return fail(ctx, JJS_ERR_ARGUMENT, "null key buffer");
     const size_t g = ctx->dev.size();
     const size_t per = (n + g - 1) / g;
+    std::vector<uint8_t*> bufs(g, nullptr);
     int rc = JJS_SUCCESS;
     for (size_t k = 0; k < g && rc == JJS_SUCCESS; k++) {
         size_t lo = k * per, hi = lo + per < n ? lo + per : n;
         if (lo >= hi) break;
-        rc = run_aggregate_shard(ctx, ctx->dev[k], pks, offsets + lo, sig + 64 * lo, msg + 32 * lo, hi - lo, status + lo,
-                                 c_out ? c_out + 32 * lo : nullptr, agg_out ? agg_out + 32 * lo : nullptr);
+        DeviceState& d = ctx->dev[k];
+        size_t m = hi - lo, K = offsets[hi] - offsets[lo];
+        cudaSetDevice(d.device);
+        // layout: keys | sig | msg | status(+pad) | c | agg | offsets
+        size_t o_sig = 32 * K, o_msg = o_sig + 64 * m, o_st = o_msg + 32 * m, o_c = o_st + ((m + 31) / 32) * 32, o_agg = o_c + 32 * m,
+               o_off = o_agg + 32 * m, total = o_off + 4 * (m + 1);
+        cudaError_t e = cudaMalloc(&bufs[k], total ? total : 4);
+        if (e != cudaSuccess) { rc = fail(ctx, JJS_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+        uint8_t* b = bufs[k];
+        if (K) cudaMemcpyAsync(b, pks + 32 * (size_t)offsets[lo], 32 * K, cudaMemcpyHostToDevice, d.stream);
+        cudaMemcpyAsync(b + o_sig, sig + 64 * lo, 64 * m, cudaMemcpyHostToDevice, d.stream);
+        cudaMemcpyAsync(b + o_msg, msg + 32 * lo, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        cudaMemcpyAsync(b + o_off, offsets + lo, 4 * (m + 1), cudaMemcpyHostToDevice, d.stream);
+        // device keys start at offsets[lo]: hand the kernels a key pointer that makes absolute offsets valid
+        rc = run_aggregate_device(ctx, d, b - 32 * (size_t)offsets[lo], reinterpret_cast<uint32_t*>(b + o_off), offsets + lo, b + o_sig, b + o_msg, m,
+                                  b + o_st, c_out ? b + o_c : nullptr, agg_out ? b + o_agg : nullptr, d.stream);
+        if (rc) break;
+        cudaMemcpyAsync(status + lo, b + o_st, m, cudaMemcpyDeviceToHost, d.stream);
+        if (c_out) cudaMemcpyAsync(c_out + 32 * lo, b + o_c, 32 * m, cudaMemcpyDeviceToHost, d.stream);
+        if (agg_out) cudaMemcpyAsync(agg_out + 32 * lo, b + o_agg, 32 * m, cudaMemcpyDeviceToHost, d.stream);
     }
     for (size_t k = 0; k < g; k++) {
         cudaSetDevice(ctx->dev[k].device);
         cudaError_t e = cudaStreamSynchronize(ctx->dev[k].stream);
         if (e != cudaSuccess && rc == JJS_SUCCESS) rc = fail(ctx, JJS_ERR_CUDA, "aggregate verify failed: %s", cudaGetErrorString(e));
+        cudaFree(bufs[k]);
     }
     return rc;
 }
@@ -510,7 +583,7 @@ void free_device(DeviceState& d) {
     cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
     cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords);
     cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
-    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.s_keys); cudaFree(d.s_agg); cudaFree(d.s_offsets);
+    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 
@@ -628,6 +701,45 @@ JJS_API int jjs_subgroup_check(jjs_ctx* ctx, const uint8_t* points32, size_t n, 
     cudaFree(d_in);
     cudaFree(d_out);
     if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "subgroup check failed: %s", cudaGetErrorString(e));
+    return JJS_SUCCESS;
+}
+JJS_API int jjs_verify_aggregate_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pks32, const uint32_t* d_offsets, const uint32_t* h_offsets,
+                                        const uint8_t* d_sig64, const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
+                                        uint8_t* d_aggpk32_or_null, void* cuda_stream) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (device_index < 0 || (size_t)device_index >= ctx->dev.size()) return fail(ctx, JJS_ERR_ARGUMENT, "device_index out of range");
+    if (n == 0) return JJS_SUCCESS;
+    if (!d_offsets || !h_offsets || !d_sig64 || !d_msg32 || !d_status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_aggregate_device(ctx, ctx->dev[device_index], d_pks32, d_offsets, h_offsets, d_sig64, d_msg32, n, d_status, d_c32_or_null,
+                                d_aggpk32_or_null, (cudaStream_t)cuda_stream);
+}
+JJS_API int jjs_sign_aggregate_batch(jjs_ctx* ctx, const uint8_t* sk32, const uint32_t* offsets, const uint8_t* rnd32, const uint8_t* msg32, size_t n,
+                                     uint8_t* pks32_out, uint8_t* sig64_out) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (n == 0) return JJS_SUCCESS;
+    if (!sk32 || !offsets || !rnd32 || !msg32 || !pks32_out || !sig64_out) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    if (offsets[0] != 0) return fail(ctx, JJS_ERR_ARGUMENT, "offsets[0] must be 0");
+    DeviceState& d = ctx->dev[0];
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    const size_t K = offsets[n];
+    uint8_t* b = nullptr;
+    size_t o_off = 32 * K, o_rnd = o_off + ((4 * (n + 1) + 31) / 32) * 32, o_msg = o_rnd + 32 * n, o_pks = o_msg + 32 * n, o_sig = o_pks + 32 * K,
+           total = o_sig + 64 * n;
+    JJS_CUDA(ctx, cudaMalloc(&b, total));
+    cudaMemcpyAsync(b, sk32, 32 * K, cudaMemcpyHostToDevice, d.stream);
+    cudaMemcpyAsync(b + o_off, offsets, 4 * (n + 1), cudaMemcpyHostToDevice, d.stream);
+    cudaMemcpyAsync(b + o_rnd, rnd32, 32 * n, cudaMemcpyHostToDevice, d.stream);
+    cudaMemcpyAsync(b + o_msg, msg32, 32 * n, cudaMemcpyHostToDevice, d.stream);
+    k_sign_aggregate<<<blocks_for(n), BLOCK, 0, d.stream>>>(b, reinterpret_cast<uint32_t*>(b + o_off), b + o_rnd, b + o_msg, n, b + o_pks, b + o_sig,
+                                                          d.tables());
+    ctx->launches++;
+    cudaMemcpyAsync(pks32_out, b + o_pks, 32 * K, cudaMemcpyDeviceToHost, d.stream);
+    cudaMemcpyAsync(sig64_out, b + o_sig, 64 * n, cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaFree(b);
+    if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "sign aggregate batch failed: %s", cudaGetErrorString(e));
     return JJS_SUCCESS;
 }
 JJS_API void jjs_profile_enable(jjs_ctx* ctx, int on) {

@@ -113,10 +113,70 @@ def invalidate(variant: int, pk, sig, msg, frac: float, seed: int, rank: int = 0
     return pk, sig, msg, expected, cls
 
 
+AGG_CLASSES = [
+    ("u_plus_one", 1), ("u_ge_r", 3), ("msg_bit_flip", 1), ("msg_ge_q", 3), ("R_from_next_item", 1), ("R_sign_flip", 1),
+    ("R_identity", 2), ("R_order8", 2), ("R_v_ge_q", 3), ("R_off_curve", 3), ("signer_key_from_next_item", 1),
+    ("signer_key_off_curve", 3), ("signer_key_v_ge_q", 3),
+]
+
+
+def make_aggregate_batch(bv: BatchVerifier, n: int, invalid_frac: float, seed: int = 0xB200, rank: int = 0, signers=(2, 3, 4)):
+    """Aggregate-key items: signer counts uniform over `signers`, signed on the GPU, then a
+    fraction invalidated.  Returns (pks[K,32], offsets[n+1], sig, msg, expected_status, class_index)."""
+    rng = np.random.default_rng([seed, rank, 7])
+    counts = rng.choice(np.asarray(signers, dtype=np.uint32), size=n)
+    offsets = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(counts, out=offsets[1:])
+    K = int(offsets[-1])
+    sk = random_scalars(rng, K, 251)
+    sk[:, 0] |= 1
+    rnd = random_scalars(rng, n, 251)
+    msg = random_scalars(rng, n, 254)
+    pks, sig = bv.sign_aggregate_batch(sk, offsets, rnd, msg)
+    expected = np.zeros(n, dtype=np.uint8)
+    cls = np.full(n, -1, dtype=np.int16)
+    k = int(round(invalid_frac * n))
+    idx = np.sort(rng.choice(n, size=k, replace=False)) if k else np.zeros(0, dtype=np.int64)
+    orig_sig, orig_pks = sig.copy(), pks.copy()
+    for j, i in enumerate(idx):
+        c = j % len(AGG_CLASSES)
+        name, st = AGG_CLASSES[c]
+        nxt = (i + 1) % n
+        if name == "u_plus_one":
+            sig[i, :32] = _le((int.from_bytes(sig[i, :32].tobytes(), "little") + 1) % R_INT)
+        elif name == "u_ge_r":
+            sig[i, :32] = U_GE_R
+        elif name == "msg_bit_flip":
+            msg[i, 0] ^= 1
+        elif name == "msg_ge_q":
+            msg[i] = M_GE_Q
+        elif name == "R_from_next_item":
+            sig[i, 32:] = orig_sig[nxt, 32:]
+        elif name == "R_sign_flip":
+            sig[i, 63] ^= 0x80
+        elif name == "R_identity":
+            sig[i, 32:] = IDENTITY
+        elif name == "R_order8":
+            sig[i, 32:] = ORDER8
+        elif name == "R_v_ge_q":
+            sig[i, 32:] = V_GE_Q
+        elif name == "R_off_curve":
+            sig[i, 32:] = OFF_CURVE
+        elif name == "signer_key_from_next_item":
+            pks[offsets[i]] = orig_pks[offsets[nxt]]
+        elif name == "signer_key_off_curve":
+            pks[offsets[i + 1] - 1] = OFF_CURVE
+        elif name == "signer_key_v_ge_q":
+            pks[offsets[i]] = V_GE_Q
+        expected[i] = st
+        cls[i] = c
+    return pks, offsets, sig, msg, expected, cls
+
+
 def make_batch(bv: BatchVerifier, variant: int, n: int, invalid_frac: float, seed: int = 0xB200, rank: int = 0):
     pk, sig, msg = make_valid(bv, variant, n, seed, rank)
     assert pk.shape == (n, PK_SIZE[variant]) and sig.shape == (n, SIG_SIZE[variant])
     return invalidate(variant, pk, sig, msg, invalid_frac, seed, rank)
 
 
-__all__ = ["make_batch", "make_valid", "invalidate", "CLASSES", "SINGLE", "DOUBLE", "VARGEN"]
+__all__ = ["make_batch", "make_aggregate_batch", "make_valid", "invalidate", "CLASSES", "AGG_CLASSES", "SINGLE", "DOUBLE", "VARGEN"]

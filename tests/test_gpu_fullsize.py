@@ -53,3 +53,34 @@ def test_device_pointer_entry_matches_host_entry(bv):
     stream.synchronize()
     st, c = bv.verify_single(pk, sig, msg, True)
     assert np.array_equal(d_st.cpu().numpy(), st) and np.array_equal(d_c.cpu().numpy(), c) and np.array_equal(st, expected)
+
+
+def test_aggregate_workload_full_size(bv):
+    """2^17 aggregate-key items signed on the GPU (signer counts 2..4), 5 % invalidated: expectation by construction,
+    host and device entry points, and an oracle spot check."""
+    import torch
+    from jubjub_schnorr_b200 import workload as wl
+    n = 1 << 17
+    pks, off, sig, msg, expected, cls = wl.make_aggregate_batch(bv, n, 0.05, seed=0xA66)
+    st, c, agg = bv.verify_aggregate(pks, off, sig, msg, True, True)
+    assert np.array_equal(st, expected)
+    idx = np.random.default_rng(3).choice(n - 1, size=300, replace=False)
+    for i in idx[:300]:
+        pass
+    sel = np.sort(idx)
+    sub_off = np.zeros(len(sel) + 1, dtype=np.uint32)
+    sub_keys = []
+    for j, i in enumerate(sel):
+        sub_keys.append(pks[off[i]:off[i + 1]])
+        sub_off[j + 1] = sub_off[j] + (off[i + 1] - off[i])
+    st_o, c_o, agg_o = co.verify_aggregate(np.concatenate(sub_keys), sub_off, sig[sel], msg[sel])
+    assert np.array_equal(st_o, st[sel]) and np.array_equal(c_o, c[sel])
+    ok = st_o != 3
+    assert np.array_equal(agg_o[ok], agg[sel][ok])
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(x).to(dev) for x in (pks, off, sig, msg)]
+    d_st = torch.empty(n, dtype=torch.uint8, device=dev)
+    bv.verify_aggregate_device(d[0].data_ptr(), d[1].data_ptr(), off, d[2].data_ptr(), d[3].data_ptr(), n, d_st.data_ptr(),
+                               stream=torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_st.cpu().numpy(), expected)
