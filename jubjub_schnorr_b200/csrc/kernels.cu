@@ -48,13 +48,16 @@ __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode(Fields fiel
 }
 
 // one thread folds the signer keys of one item into its aggregate key (slot 0 of the single-variant point arrays)
+// `order` lists the items sorted by signer count, so the lanes of a warp loop over the same number of signers
 __global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, const uint32_t* offsets,
-                                                     uint32_t key_base, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags, uint8_t* agg_out, fq* tab,
-                                                     size_t stride) {
-    size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= n) return;
+                                                     const uint32_t* order, uint32_t key_base, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags,
+                                                     uint8_t* agg_out, fq* tab, size_t stride) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    size_t item = order[t];
     uint32_t w[8];
-    stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + item, stride);
+    stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + t,
+                    tab + 36 * stride + t, stride);
     if (agg_out) {
         uint4* o = reinterpret_cast<uint4*>(agg_out + item * 32);
         o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -230,6 +233,10 @@ struct DeviceState {
     fq *keys_u = nullptr, *keys_v = nullptr;
     uint8_t* kflags = nullptr;
     size_t cap_keys = 0;
+    uint32_t* d_order = nullptr;   // items of a chunk sorted by signer count
+    std::vector<uint32_t> h_order;
+    uint8_t* agg_stage = nullptr;  // grow-only staging of the aggregate-key host path
+    size_t agg_stage_bytes = 0;
     // staging for the host-buffer entry points
     uint8_t *s_pk = nullptr, *s_sig = nullptr, *s_msg = nullptr, *s_status = nullptr, *s_c = nullptr;
     size_t stage_items = 0;
@@ -453,9 +460,26 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
         if (K) k_decode<<<blocks_for(K), BLOCK, 0, stream>>>(fk, 1, 0, K, d.keys_u, d.keys_v, d.kflags, T, false);
         k_decode<<<blocks_for(m), BLOCK, 0, stream>>>(fr, 1, 1, m, d.pts_u, d.pts_v, d.pflags, T, true);
         t0.stop(stream);
+        // counting sort of the chunk's items by signer count (host side; counts above 63 share the last bucket)
+        {
+            size_t hist[65] = {0};
+            for (size_t i = 0; i < m; i++) {
+                uint32_t c = h_offsets[off + i + 1] - h_offsets[off + i];
+                hist[(c > 63 ? 63 : c) + 1]++;
+            }
+            for (int b = 0; b < 64; b++) hist[b + 1] += hist[b];
+            d.h_order.resize(m);
+            for (size_t i = 0; i < m; i++) {
+                uint32_t c = h_offsets[off + i + 1] - h_offsets[off + i];
+                d.h_order[hist[c > 63 ? 63 : c]++] = (uint32_t)i;
+            }
+            if (!d.d_order) JJS_CUDA(ctx, cudaMalloc(&d.d_order, sizeof(uint32_t) * CHUNK_ITEMS));
+            JJS_CUDA(ctx, cudaStreamSynchronize(stream));  // h_order is reused by the next chunk / call
+            JJS_CUDA(ctx, cudaMemcpyAsync(d.d_order, d.h_order.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, stream));
+        }
         StageTimer t2(ctx, d.device, 2, stream);
-        k_aggregate<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, key_lo, m, d.pts_u, d.pts_v, d.pflags,
-                                                        d_agg ? d_agg + 32 * off : nullptr, d.tab, TAB_THREADS);
+        k_aggregate<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, d.d_order, key_lo, m, d.pts_u, d.pts_v,
+                                                        d.pflags, d_agg ? d_agg + 32 * off : nullptr, d.tab, TAB_THREADS);
         t2.stop(stream);
         StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
@@ -486,7 +510,6 @@ int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, con
     if (offsets[n] > offsets[0] && !pks) return fail(ctx, JJS_ERR_ARGUMENT, "null key buffer");
     const size_t g = ctx->dev.size();
     const size_t per = (n + g - 1) / g;
-    std::vector<uint8_t*> bufs(g, nullptr);
     int rc = JJS_SUCCESS;
     for (size_t k = 0; k < g && rc == JJS_SUCCESS; k++) {
         size_t lo = k * per, hi = lo + per < n ? lo + per : n;
@@ -497,9 +520,16 @@ int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, con
         // layout: keys | sig | msg | status(+pad) | c | agg | offsets
         size_t o_sig = 32 * K, o_msg = o_sig + 64 * m, o_st = o_msg + 32 * m, o_c = o_st + ((m + 31) / 32) * 32, o_agg = o_c + 32 * m,
                o_off = o_agg + 32 * m, total = o_off + 4 * (m + 1);
-        cudaError_t e = cudaMalloc(&bufs[k], total ? total : 4);
-        if (e != cudaSuccess) { rc = fail(ctx, JJS_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
-        uint8_t* b = bufs[k];
+        if (total > d.agg_stage_bytes) {
+            cudaStreamSynchronize(d.stream);
+            cudaFree(d.agg_stage);
+            d.agg_stage = nullptr;
+            d.agg_stage_bytes = 0;
+            cudaError_t e = cudaMalloc(&d.agg_stage, total);
+            if (e != cudaSuccess) { rc = fail(ctx, JJS_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+            d.agg_stage_bytes = total;
+        }
+        uint8_t* b = d.agg_stage;
         if (K) cudaMemcpyAsync(b, pks + 32 * (size_t)offsets[lo], 32 * K, cudaMemcpyHostToDevice, d.stream);
         cudaMemcpyAsync(b + o_sig, sig + 64 * lo, 64 * m, cudaMemcpyHostToDevice, d.stream);
         cudaMemcpyAsync(b + o_msg, msg + 32 * lo, 32 * m, cudaMemcpyHostToDevice, d.stream);
@@ -516,7 +546,6 @@ int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, con
         cudaSetDevice(ctx->dev[k].device);
         cudaError_t e = cudaStreamSynchronize(ctx->dev[k].stream);
         if (e != cudaSuccess && rc == JJS_SUCCESS) rc = fail(ctx, JJS_ERR_CUDA, "aggregate verify failed: %s", cudaGetErrorString(e));
-        cudaFree(bufs[k]);
     }
     return rc;
 }
@@ -583,7 +612,7 @@ void free_device(DeviceState& d) {
     cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
     cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords);
     cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
-    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags);
+    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.agg_stage); cudaFree(d.d_order);
     if (d.stream) cudaStreamDestroy(d.stream);
 }
 

@@ -180,37 +180,47 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
 // d_j = H_trunc(pk_j || pk_0 .. pk_{n-1}),  agg = sum_j d_j * pk_j.  Like the reference, the signer keys are NOT
 // validated (only decoded); the aggregate is then treated exactly as the PublicKey of a single verification: its
 // affine coordinates, validity flags (identity, torsion freeness) and wire encoding are written to slot `out_index`.
+JJS_HD void aggregate_coeff(int8_t* digits, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j) {
+    Sponge sp;
+    sponge_start(sp, (int)(2 + 2 * (hi - lo)));
+    sponge_absorb(sp, keys_u[j]);
+    sponge_absorb(sp, keys_v[j]);
+#pragma unroll 1
+    for (uint32_t k = lo; k < hi; k++) {
+        sponge_absorb(sp, keys_u[k]);
+        sponge_absorb(sp, keys_v[k]);
+    }
+    uint32_t d[8];
+    sponge_squeeze_truncated(d, sp);
+    recode_signed16(digits, d);
+}
+
 JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
-                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride) {
+                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tabA, fq* tabB, size_t stride) {
     bool decoded = true;
     for (uint32_t j = lo; j < hi; j++) decoded = decoded && (kflags[j] & PF_DECODED);
-    uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (!decoded || 2 + 2 * (hi - lo) > JJS_MAX_ABSORB) {
         out_flags[out_index] = 0;
         if (agg_wire)
-            for (int i = 0; i < 8; i++) agg_wire[i] = zero[i];
+            for (int i = 0; i < 8; i++) agg_wire[i] = 0;
         return;
     }
     ext acc;
     ext_identity(acc);
+    // signers are folded two at a time so that each pair shares its 252 doublings (Straus)
 #pragma unroll 1
-    for (uint32_t j = lo; j < hi; j++) {
-        Sponge sp;
-        sponge_start(sp, (int)(2 + 2 * (hi - lo)));
-        sponge_absorb(sp, keys_u[j]);
-        sponge_absorb(sp, keys_v[j]);
-#pragma unroll 1
-        for (uint32_t k = lo; k < hi; k++) {
-            sponge_absorb(sp, keys_u[k]);
-            sponge_absorb(sp, keys_v[k]);
-        }
-        uint32_t d[8];
-        sponge_squeeze_truncated(d, sp);
-        int8_t digits[64];
-        recode_signed16(digits, d);
-        varbase_table_build(tab, stride, keys_u[j], keys_v[j]);
+    for (uint32_t j = lo; j < hi; j += 2) {
+        int8_t dA[64], dB[64];
         ext term, sum;
-        varbase_mul<true>(term, tab, stride, digits);
+        aggregate_coeff(dA, keys_u, keys_v, lo, hi, j);
+        varbase_table_build(tabA, stride, keys_u[j], keys_v[j]);
+        if (j + 1 < hi) {
+            aggregate_coeff(dB, keys_u, keys_v, lo, hi, j + 1);
+            varbase_table_build(tabB, stride, keys_u[j + 1], keys_v[j + 1]);
+            straus2<64>(term, tabA, tabB, stride, dA, dB);
+        } else {
+            varbase_mul<true>(term, tabA, stride, dA);
+        }
         pniels nt;
         ext_to_pniels(nt, term);
         ext_add_pniels<true>(sum, acc, nt);

@@ -160,7 +160,7 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
     for (size_t k = 0; k < K; k++) stage_decode(fk, k, ku.data(), kv.data(), kf.data(), k, g_tables);
     for (size_t i = 0; i < n; i++) {
         uint32_t w[8];
-        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1);
+        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), tab.data() + 36, 1);
         memcpy(agg_out + 32 * i, w, 32);
         stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables);
         stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
