@@ -97,6 +97,21 @@ int jjs_verify_aggregate_device(jjs_ctx* ctx, int device_index, const uint8_t* d
                                 const uint32_t* h_offsets, const uint8_t* d_sig64, const uint8_t* d_msg32, size_t n,
                                 uint8_t* d_status, uint8_t* d_c32_or_null, uint8_t* d_aggpk32_or_null, void* cuda_stream);
 
+/* Typed inputs (what a Rust caller holds before any to_bytes()): every point is given by its JubJubExtended
+ * coordinates (u, v, z, t1, t2), each the in-memory BlsScalar of the reference (4 x u64 little-endian Montgomery limbs,
+ * R = 2^256): 160 bytes per point.  points_ext160 is item-major, the points of one item in the order
+ *   variant 0: PK, R        variant 1: PK, PK', R, R'        variant 2: PK, generator, R
+ * u32 = JubJubScalar::to_bytes() of the signature scalar, msg32 = BlsScalar::to_bytes().  The GPU normalises the points
+ * (no per-point inversion on the CPU), applies is_valid() exactly as verify() does for typed values -- z != 0, curve
+ * equation, t1 t2 consistency, identity, torsion -- and then runs the same pipeline.  Status 3 is returned when u32 / msg32
+ * is not canonical or a coordinate is not a reduced field element.  Host buffers. */
+int jjs_verify_ext(jjs_ctx* ctx, int variant, const uint8_t* points_ext160, const uint8_t* u32, const uint8_t* msg32,
+                   size_t n, uint8_t* status, uint8_t* c32_or_null);
+
+/* Test-data utility for the typed path: wire point i -> the 160-byte coordinates (u z, v z, z, u z, v) with the caller's
+ * Montgomery value z (z_mont32, any non-zero reduced field element); zeros if the point does not decode.  Host buffers. */
+int jjs_points_to_ext(jjs_ctx* ctx, const uint8_t* points32, const uint8_t* z_mont32, size_t n, uint8_t* out160);
+
 /* Challenge hash only (hash parity hook): c = challenge_hash(..) for already-valid encodings, no curve
  * check.  variant: 0 single, 1 double, 2 var-generator.  Host buffers. */
 int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32,

@@ -119,6 +119,25 @@ class BatchVerifier:
             out.append(agg)
         return out[0] if len(out) == 1 else tuple(out)
 
+    def verify_ext(self, variant, points_ext160, u32, msg32, want_challenge=False):
+        """Typed inputs: points as JubJubExtended Montgomery coordinates (160 bytes each, item-major), see jjs_verify_ext."""
+        slots = {SINGLE: 2, DOUBLE: 4, VARGEN: 3}[variant]
+        pts, u, msg = _u8(points_ext160, 160 * slots, "points"), _u8(u32, 32, "u"), _u8(msg32, 32, "msg")
+        n = msg.shape[0]
+        if pts.shape[0] != n or u.shape[0] != n:
+            raise ValueError("points, u and msg must describe the same number of items")
+        status = np.empty(n, dtype=np.uint8)
+        c = np.empty((n, 32), dtype=np.uint8) if want_challenge else None
+        self._check(self._lib.jjs_verify_ext(self._ctx, variant, pts.ctypes.data, u.ctypes.data, msg.ctypes.data, n, status.ctypes.data,
+                                             c.ctypes.data if want_challenge else None), "jjs_verify_ext")
+        return (status, c) if want_challenge else status
+
+    def points_to_ext(self, points32, z_mont32):
+        pts, z = _u8(points32, 32, "points"), _u8(z_mont32, 32, "z")
+        out = np.empty((pts.shape[0], 160), dtype=np.uint8)
+        self._check(self._lib.jjs_points_to_ext(self._ctx, pts.ctypes.data, z.ctypes.data, pts.shape[0], out.ctypes.data), "jjs_points_to_ext")
+        return out
+
     def challenge_only(self, variant, pk, sig, msg32):
         pk, sig, msg = _u8(pk, PK_SIZE[variant], "pk"), _u8(sig, SIG_SIZE[variant], "sig"), _u8(msg32, 32, "msg")
         n = msg.shape[0]

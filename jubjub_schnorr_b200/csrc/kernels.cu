@@ -47,6 +47,38 @@ __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode(Fields fiel
     stage_decode(fields.f[slot], item, pts_u, pts_v, pflags, (size_t)(slot_base + slot) * n + item, T, want_subgroup);
 }
 
+// typed inputs: thread t < slots * n normalises point t % slots of item t / slots (item-major, 160 bytes per point)
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode_ext(const uint8_t* pts, int slots, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)slots * n) return;
+    int slot = (int)(t / n);
+    size_t item = t - (size_t)slot * n;
+    stage_decode_ext(WireField{pts + 160 * (size_t)slot, (uint32_t)(160 * slots)}, item, pts_u, pts_v, pflags, (size_t)slot * n + item);
+}
+
+// test-data utility: wire point -> JubJubExtended coordinates (u z, v z, z, u z, v) for a caller-chosen Montgomery z
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_points_to_ext(const uint8_t* pts32, const uint8_t* z32, size_t n, uint8_t* out160, Tables T) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    fq u, v, z, c[5];
+    wire_load(w, WireField{pts32, 32}, i);
+    bool ok = point_from_wire(u, v, w, T);
+    wire_load(z.l, WireField{z32, 32}, i);
+    ok = ok && !ge_q(z.l);
+    fq_mul(c[0], u, z);
+    fq_mul(c[1], v, z);
+    c[2] = z;
+    c[3] = c[0];
+    c[4] = v;
+    uint4* o = reinterpret_cast<uint4*>(out160 + 160 * i);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        o[2 * k] = ok ? make_uint4(c[k].l[0], c[k].l[1], c[k].l[2], c[k].l[3]) : make_uint4(0, 0, 0, 0);
+        o[2 * k + 1] = ok ? make_uint4(c[k].l[4], c[k].l[5], c[k].l[6], c[k].l[7]) : make_uint4(0, 0, 0, 0);
+    }
+}
+
 // one thread folds the signer keys of one item into its aggregate key (slot 0 of the single-variant point arrays)
 // `order` lists the items sorted by signer count, so the lanes of a warp loop over the same number of signers
 __global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, const uint32_t* offsets,
@@ -550,6 +582,66 @@ int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, con
     return rc;
 }
 
+// typed inputs: points as JubJubExtended coordinates, scalars as canonical bytes; host buffers, device 0
+int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, const uint8_t* msg, size_t n, uint8_t* status, uint8_t* c_out) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
+    if (n == 0) return JJS_SUCCESS;
+    if (!pts || !u32 || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    const int slots = variant_slots(variant), neq = variant == VAR_DOUBLE ? 2 : 1;
+    const size_t g = ctx->dev.size(), per = (n + g - 1) / g;
+    int rc = JJS_SUCCESS;
+    for (size_t k = 0; k < g && rc == JJS_SUCCESS; k++) {
+        size_t lo = k * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        DeviceState& d = ctx->dev[k];
+        rc = ensure_scratch(ctx, d);
+        if (rc) break;
+        cudaSetDevice(d.device);
+        Tables T = d.tables();
+        for (size_t off = lo; off < hi && rc == JJS_SUCCESS; off += CHUNK_ITEMS) {
+            size_t m = hi - off < CHUNK_ITEMS ? hi - off : CHUNK_ITEMS;
+            size_t need = m * (160 * (size_t)slots + 32 + 32 + 1 + 32);
+            if (need > d.agg_stage_bytes) {
+                cudaStreamSynchronize(d.stream);
+                cudaFree(d.agg_stage);
+                d.agg_stage = nullptr;
+                d.agg_stage_bytes = 0;
+                cudaError_t e = cudaMalloc(&d.agg_stage, need);
+                if (e != cudaSuccess) { rc = fail(ctx, JJS_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+                d.agg_stage_bytes = need;
+            }
+            uint8_t *b_pts = d.agg_stage, *b_u = b_pts + 160 * (size_t)slots * m, *b_msg = b_u + 32 * m, *b_c = b_msg + 32 * m, *b_st = b_c + 32 * m;
+            cudaMemcpyAsync(b_pts, pts + 160 * (size_t)slots * off, 160 * (size_t)slots * m, cudaMemcpyHostToDevice, d.stream);
+            cudaMemcpyAsync(b_u, u32 + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+            cudaMemcpyAsync(b_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+            WireField fmsg{b_msg, 32}, fu{b_u, 32};
+            StageTimer t0(ctx, d.device, 0, d.stream);
+            k_decode_ext<<<blocks_for(slots * m), BLOCK, 0, d.stream>>>(b_pts, slots, m, d.pts_u, d.pts_v, d.pflags);
+            t0.stop(d.stream);
+            StageTimer t1(ctx, d.device, 1, d.stream);
+            k_challenge<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
+            t1.stop(d.stream);
+            StageTimer t3(ctx, d.device, 3, d.stream);
+            for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
+                size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
+                k_equation<<<blocks_for(cnt), BLOCK, 0, d.stream>>>(variant, d.pts_u, d.pts_v, d.pflags, d.iflags, m, first, cnt, fu, d.cwords, d.eqflags,
+                                                                   d.tab, TAB_THREADS, T);
+                ctx->launches++;
+            }
+            t3.stop(d.stream);
+            k_finalize<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, b_st, c_out ? b_c : nullptr);
+            ctx->launches += 3;
+            cudaMemcpyAsync(status + off, b_st, m, cudaMemcpyDeviceToHost, d.stream);
+            if (c_out) cudaMemcpyAsync(c_out + 32 * off, b_c, 32 * m, cudaMemcpyDeviceToHost, d.stream);
+            cudaError_t e = cudaStreamSynchronize(d.stream);  // the staging buffer is reused by the next chunk
+            if (e != cudaSuccess) rc = fail(ctx, JJS_ERR_CUDA, "typed verify failed: %s", cudaGetErrorString(e));
+        }
+    }
+    return rc;
+}
+
 int run_sign(jjs_ctx* ctx, int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, size_t n, uint8_t* pk_out,
              uint8_t* sig_out) {
     if (!ctx) return JJS_ERR_ARGUMENT;
@@ -769,6 +861,29 @@ JJS_API int jjs_sign_aggregate_batch(jjs_ctx* ctx, const uint8_t* sk32, const ui
     cudaError_t e = cudaStreamSynchronize(d.stream);
     cudaFree(b);
     if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "sign aggregate batch failed: %s", cudaGetErrorString(e));
+    return JJS_SUCCESS;
+}
+JJS_API int jjs_verify_ext(jjs_ctx* ctx, int variant, const uint8_t* points_ext160, const uint8_t* u32, const uint8_t* msg32, size_t n,
+                           uint8_t* status, uint8_t* c32_or_null) {
+    return run_ext(ctx, variant, points_ext160, u32, msg32, n, status, c32_or_null);
+}
+JJS_API int jjs_points_to_ext(jjs_ctx* ctx, const uint8_t* points32, const uint8_t* z_mont32, size_t n, uint8_t* out160) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (n == 0) return JJS_SUCCESS;
+    if (!points32 || !z_mont32 || !out160) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    DeviceState& d = ctx->dev[0];
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    uint8_t* b = nullptr;
+    JJS_CUDA(ctx, cudaMalloc(&b, n * (32 + 32 + 160)));
+    cudaMemcpyAsync(b, points32, 32 * n, cudaMemcpyHostToDevice, d.stream);
+    cudaMemcpyAsync(b + 32 * n, z_mont32, 32 * n, cudaMemcpyHostToDevice, d.stream);
+    k_points_to_ext<<<blocks_for(n), BLOCK, 0, d.stream>>>(b, b + 32 * n, n, b + 64 * n, d.tables());
+    ctx->launches++;
+    cudaMemcpyAsync(out160, b + 64 * n, 160 * n, cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    cudaFree(b);
+    if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "points_to_ext failed: %s", cudaGetErrorString(e));
     return JJS_SUCCESS;
 }
 JJS_API void jjs_profile_enable(jjs_ctx* ctx, int on) {

@@ -58,6 +58,50 @@ JJS_HD void stage_decode(const WireField& f, size_t item, fq* out_u, fq* out_v, 
     out_flags[slot_index] = fl;
 }
 
+// ---- stage 1 (typed inputs): one point given as JubJubExtended coordinates (u, v, z, t1, t2) -------------------
+// Each coordinate is the in-memory BlsScalar of the reference (4 x u64 little-endian Montgomery limbs, R = 2^256),
+// 160 bytes per point.  Mirrors what verify() sees for a typed value (dusk-jubjub semantics):
+//   is_on_curve   = z != 0  and  the affine point (u/z, v/z) satisfies the curve equation  and  (u/z)(v/z) z == t1 t2
+//   is_identity   = u == 0 and v == z
+//   is_torsion_free on the affine point (meaningful only when on the curve; the three are AND-ed by is_valid()).
+// A coordinate that is not a reduced field element is reported as undecodable.
+JJS_HD void stage_decode_ext(const WireField& f, size_t item, fq* out_u, fq* out_v, uint8_t* out_flags, size_t slot_index) {
+    fq c[5];
+    bool reduced = true;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        WireField fk{f.base + 32 * k, f.stride};
+        wire_load(c[k].l, fk, item);
+        reduced = reduced && !ge_q(c[k].l);
+    }
+    if (!reduced) {
+        out_flags[slot_index] = 0;
+        return;
+    }
+    fq zi, au, av, u2, v2, lhs, rhs, one, d, t;
+    fq_inv(zi, c[2]);
+    fq_mul(au, c[0], zi);
+    fq_mul(av, c[1], zi);
+    fq_sqr(u2, au);
+    fq_sqr(v2, av);
+    fq_sub(lhs, v2, u2);
+    fq_one(one);
+    fq_load_const(d, JJS_C(EDWARDS_D));
+    fq_mul(rhs, u2, v2);
+    fq_mul(rhs, rhs, d);
+    fq_add(rhs, rhs, one);
+    bool on_curve = !fq_is_zero(c[2]) && fq_eq(lhs, rhs);
+    fq_mul(t, au, av);
+    fq_mul(t, t, c[2]);
+    fq_mul(lhs, c[3], c[4]);
+    on_curve = on_curve && fq_eq(t, lhs);
+    uint8_t fl = PF_DECODED | ((fq_is_zero(c[0]) && fq_eq(c[1], c[2])) ? PF_IDENTITY : 0);
+    if (on_curve && point_is_torsion_free_tate(au, av)) fl |= PF_TORSION_FREE;
+    out_u[slot_index] = au;
+    out_v[slot_index] = av;
+    out_flags[slot_index] = fl;
+}
+
 // ---- stage 2: challenge hash -------------------------------------------------------------------
 // pts_u / pts_v are [slots][n]; writes the challenge as 8 little-endian words and the scalar-range flag.
 JJS_HD void stage_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n, size_t item,

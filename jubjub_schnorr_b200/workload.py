@@ -173,6 +173,24 @@ def make_aggregate_batch(bv: BatchVerifier, n: int, invalid_frac: float, seed: i
     return pks, offsets, sig, msg, expected, cls
 
 
+def make_typed_single_batch(bv: BatchVerifier, n: int, invalid_frac: float, seed: int = 0xB200, rank: int = 0):
+    """Typed single-signature items (jjs_verify_ext): a wire batch whose point fields all decode, converted on the GPU
+    to JubJubExtended coordinates with random z.  Returns (points[n,320], u[n,32], msg, expected_status)."""
+    decodable = [i for i, (name, _) in enumerate(CLASSES) if name not in ("pk_v_ge_q", "R_v_ge_q", "R_off_curve", "pk_off_curve")]
+    pk, sig, msg = make_valid(bv, SINGLE, n, seed, rank)
+    pk, sig, msg, expected, cls = invalidate(SINGLE, pk, sig, msg, invalid_frac, seed, rank)
+    undec = (cls >= 0) & ~np.isin(cls, decodable)
+    # undecodable encodings cannot be typed: restore those items to their valid form
+    pk0, sig0, msg0 = make_valid(bv, SINGLE, n, seed, rank)
+    pk[undec], sig[undec], msg[undec], expected[undec] = pk0[undec], sig0[undec], msg0[undec], 0
+    rng = np.random.default_rng([seed, rank, 31])
+    z = random_scalars(rng, 2 * n, 254)
+    z[:, 0] |= 1
+    pts = bv.points_to_ext(np.concatenate([pk, sig[:, 32:]]), z)
+    points = np.concatenate([pts[:n], pts[n:]], axis=1)
+    return np.ascontiguousarray(points), np.ascontiguousarray(sig[:, :32]), msg, expected
+
+
 def make_batch(bv: BatchVerifier, variant: int, n: int, invalid_frac: float, seed: int = 0xB200, rank: int = 0):
     pk, sig, msg = make_valid(bv, variant, n, seed, rank)
     assert pk.shape == (n, PK_SIZE[variant]) and sig.shape == (n, SIG_SIZE[variant])

@@ -125,6 +125,27 @@ def gen_aggregate(seed, signers, first=0, threads=0):
     return pks, offsets, sig, msg
 
 
+def verify_ext(variant, pts160, u32, msg32):
+    """Typed inputs (JubJubExtended Montgomery coordinates, 160 bytes per point, item-major); single-threaded."""
+    slots = {0: 2, 1: 4, 2: 3}[variant]
+    pts, u, msg = _u8(pts160, 160 * slots), _u8(u32, 32), _u8(msg32, 32)
+    n = msg.shape[0]
+    status = np.zeros(n, dtype=np.uint8)
+    c = np.zeros((n, 32), dtype=np.uint8)
+    f = lib().jjo_verify_ext
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    f.restype = None
+    f(variant, _p(pts), _p(u), _p(msg), n, _p(status), _p(c))
+    return status, c
+
+
+def point_to_ext(p32, z_mont: int):
+    """Compressed point -> 160-byte JubJubExtended coordinates (u z, v z, z, u z, v) with Montgomery scale z_mont."""
+    out = (C.c_uint8 * 160)()
+    ok = lib().jjo_point_to_ext(_b32(p32), _b32(z_mont.to_bytes(32, "little")), out)
+    return bytes(out) if ok else None
+
+
 def _b32(b):
     return (C.c_uint8 * len(b)).from_buffer_copy(bytes(b))
 

@@ -505,6 +505,65 @@ static int verify_aggregate_one(const uint8_t *pks32, int n, const uint8_t sig64
     return st;
 }
 
+/* Typed inputs: a point as JubJubExtended coordinates (u, v, z, t1, t2), each a 32-byte little-endian Montgomery value.
+ * is_valid() as verify() evaluates it on typed values (dusk-jubjub semantics). */
+static int ext5_load(pt *p, int *valid, const uint8_t in[160]) {
+    fe c[5];
+    for (int k = 0; k < 5; k++) {
+        memcpy(c[k].l, in + 32 * k, 32);
+        if (ge256(c[k].l, JJO_Q)) return 0; /* not a reduced field element */
+    }
+    p->X = c[0]; p->Y = c[1]; p->Z = c[2];
+    Q_MUL(&p->T, &c[3], &c[4]);
+    /* is_on_curve: z != 0, affine equation, (u/z)(v/z) z == t1 t2 */
+    int on = !f_is_zero(&c[2]);
+    fe u, v, t;
+    pt_to_affine(&u, &v, p);
+    pt a;
+    pt_from_affine(&a, &u, &v);
+    on = on && pt_is_on_curve(&a);
+    Q_MUL(&t, &u, &v); Q_MUL(&t, &t, &c[2]);
+    on = on && f_eq(&t, &p->T);
+    int ident = pt_is_identity(p);
+    *valid = on && !ident && pt_is_torsion_free(&a);
+    return 1;
+}
+static int verify_ext_one(int variant, const uint8_t *pts, const uint8_t u32[32], const uint8_t msg32[32], uint8_t c_out[32]) {
+    const int slots = variant == 0 ? 2 : (variant == 1 ? 4 : 3);
+    pt p[4];
+    int valid[4], ok = 1, all_valid = 1;
+    fe u, m;
+    if (c_out) memset(c_out, 0, 32);
+    for (int s = 0; s < slots; s++) ok &= ext5_load(&p[s], &valid[s], pts + 160 * s);
+    ok &= f_from_bytes(&FR, &u, u32);
+    ok &= f_from_bytes(&FQ, &m, msg32);
+    if (!ok) return ST_BYTES_ERROR;
+    for (int s = 0; s < slots; s++) all_valid &= valid[s];
+    if (!all_valid) return ST_INVALID_POINT;
+    fe in[10], c;
+    pt a, b, s1, s2;
+    if (variant == 0) {
+        pt_to_affine(&in[0], &in[1], &p[1]); pt_to_affine(&in[2], &in[3], &p[0]); in[4] = m;
+        poseidon_hash_truncated(&c, c_out, in, 5);
+        pt_mul(&a, &G_PT, &u); pt_mul(&b, &p[0], &c); pt_add(&s1, &a, &b);
+        return pt_eq(&s1, &p[1]) ? ST_OK : ST_INVALID_SIGNATURE;
+    }
+    if (variant == 1) {
+        uint64_t tag[4] = {0x4a4a53434844424cULL, 0, 0, 0};
+        f_from_raw(&FQ, &in[0], tag);
+        pt_to_affine(&in[1], &in[2], &p[2]); pt_to_affine(&in[3], &in[4], &p[3]);
+        pt_to_affine(&in[5], &in[6], &p[0]); pt_to_affine(&in[7], &in[8], &p[1]); in[9] = m;
+        poseidon_hash_truncated(&c, c_out, in, 10);
+        pt_mul(&a, &G_PT, &u); pt_mul(&b, &p[0], &c); pt_add(&s1, &a, &b);
+        pt_mul(&a, &GN_PT, &u); pt_mul(&b, &p[1], &c); pt_add(&s2, &a, &b);
+        return (pt_eq(&s1, &p[2]) && pt_eq(&s2, &p[3])) ? ST_OK : ST_INVALID_SIGNATURE;
+    }
+    pt_to_affine(&in[0], &in[1], &p[2]); pt_to_affine(&in[2], &in[3], &p[0]); pt_to_affine(&in[4], &in[5], &p[1]); in[6] = m;
+    poseidon_hash_truncated(&c, c_out, in, 7);
+    pt_mul(&a, &p[1], &u); pt_mul(&b, &p[0], &c); pt_add(&s1, &a, &b);
+    return pt_eq(&s1, &p[2]) ? ST_OK : ST_INVALID_SIGNATURE;
+}
+
 /* ------------------------------------------------------------------ deterministic synthetic batches */
 static uint64_t splitmix64(uint64_t *s) {
     uint64_t z = (*s += 0x9e3779b97f4a7c15ULL);
@@ -748,6 +807,28 @@ EXPORT void jjo_gen_aggregate(uint64_t seed, uint64_t first, size_t n, const uin
                               uint8_t *msg32, int threads) {
     job j = {0}; j.kind = 13; j.seed = seed; j.first = first; j.offsets = offsets; j.opk = pks32; j.osig = sig64; j.omsg = msg32;
     run(&j, n, threads);
+}
+
+EXPORT void jjo_verify_ext(int variant, const uint8_t *pts160, const uint8_t *u32, const uint8_t *msg32, size_t n, uint8_t *status,
+                           uint8_t *c32_or_null) {
+    init();
+    const size_t slots = variant == 0 ? 2 : (variant == 1 ? 4 : 3);
+    for (size_t i = 0; i < n; i++)
+        status[i] = (uint8_t)verify_ext_one(variant, pts160 + 160 * slots * i, u32 + 32 * i, msg32 + 32 * i, c32_or_null ? c32_or_null + 32 * i : NULL);
+}
+/* compressed point -> JubJubExtended coordinates scaled by the Montgomery value z_mont (any non-zero field element),
+ * with t1 = u z, t2 = v (so that t1 t2 / z = u v z as required); used to build typed test inputs */
+EXPORT int jjo_point_to_ext(const uint8_t in32[32], const uint8_t z_mont32[32], uint8_t out160[160]) {
+    init();
+    pt p;
+    if (!pt_decode(&p, in32)) return 0;
+    fe z, c[5];
+    memcpy(z.l, z_mont32, 32);
+    if (ge256(z.l, JJO_Q)) return 0;
+    Q_MUL(&c[0], &p.X, &z); Q_MUL(&c[1], &p.Y, &z); c[2] = z;
+    c[3] = c[0]; c[4] = p.Y;
+    for (int k = 0; k < 5; k++) memcpy(out160 + 32 * k, c[k].l, 32);
+    return 1;
 }
 
 /* small helpers for building adversarial inputs and for unit parity checks */

@@ -185,6 +185,35 @@ int hs_subgroup(const uint8_t* p32, int method) {
     std::vector<fq> tab(36);
     return subgroup_check(WireField{p32, 32}, 0, method, tab.data(), 1, g_tables);
 }
+// typed inputs through the stage functions (single variant): pts = n x 2 x 160 bytes
+void hs_verify_ext(int variant, const uint8_t* pts, const uint8_t* u32, const uint8_t* msg, size_t n, uint8_t* status, uint8_t* c_out) {
+    ensure_ready();
+    const int slots = variant_slots(variant);
+    std::vector<fq> pu(slots * n), pv(slots * n), tab(72);
+    std::vector<uint8_t> pf(slots * n), itf(n);
+    std::vector<uint32_t> cw(8 * n);
+    WireField fmsg{msg, 32}, fu{u32, 32};
+    for (int s = 0; s < slots; s++)
+        for (size_t i = 0; i < n; i++)
+            stage_decode_ext(WireField{pts + 160 * s, (uint32_t)(160 * slots)}, i, pu.data(), pv.data(), pf.data(), s * n + i);
+    for (size_t i = 0; i < n; i++) {
+        stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
+        bool all = (itf[i] & IF_SCALARS_OK);
+        for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);
+        if (all) {
+            if (variant == VAR_SINGLE) {
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
+            } else if (variant == VAR_DOUBLE) {
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
+                if (stage_equation(pu.data(), pv.data(), n, i, 1, 3, -1, g_tables.fb_gn, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ1_OK;
+            } else {
+                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, 1, nullptr, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
+            }
+        }
+        status[i] = stage_status(variant, pf.data(), itf[i], n, i);
+        if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
+    }
+}
 int hs_sign(int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, uint8_t* pk_out, uint8_t* sig_out) {
     ensure_ready();
     uint32_t a[8], b[8], g[8] = {0}, m[8], pk[16], sig[24];

@@ -137,3 +137,25 @@ def test_gpu_signing_matches_reference_vectors(bv):
     sk, g, m, rnd = rng.random_fr(), rng.random_fr(), rng.random_fq(), rng.random_fr()
     pk, sig = bv.sign_batch(2, _a(o.le32(sk)), _a(o.le32(rnd)), _a(o.le32(m)), _a(o.le32(g)))
     assert o.b58encode(pk.tobytes()) == s["serde_public_key_var_gen"] and o.b58encode(sig.tobytes()) == s["serde_signature_var_gen"]
+
+
+@pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
+def test_typed_inputs_match_oracle(bv, vi, kind):
+    """jjs_verify_ext: JubJubExtended coordinates in, same statuses and challenges as the wire path,
+    plus the typed-only failure modes."""
+    from tests import typed_inputs as ti
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    gver = {"single": bv.verify_single, "double": bv.verify_double, "vargen": bv.verify_vargen}[kind]
+    n = 1500
+    pk, sig, msg = gen(0x7E, n)
+    pk, sig, msg, _, _ = adv.make_adversarial(kind, pk, sig, msg, seed=3, frac=0.4)
+    st_wire, c_wire = gver(pk, sig, msg, True)
+    pts, u, keep = ti.to_typed(vi, pk, sig, msg, seed=4)
+    pts, u, msg_k = pts[keep], u[keep], msg[keep]
+    st_g, c_g = bv.verify_ext(vi, pts, u, msg_k, True)
+    assert np.array_equal(st_g, st_wire[keep]) and np.array_equal(c_g, c_wire[keep])
+    bad, expected = ti.corrupt_typed(pts, st_g, seed=5)
+    st_o, c_o = co.verify_ext(vi, bad, u, msg_k)
+    st_b, c_b = bv.verify_ext(vi, bad, u, msg_k, True)
+    assert np.array_equal(st_b, st_o) and np.array_equal(c_b, c_o)
+    assert set(st_b.tolist()) == {0, 1, 2, 3}

@@ -197,3 +197,31 @@ def test_aggregate_twin(L):
     assert np.array_equal(hst, st) and np.array_equal(hc, c)
     ok = st != 3
     assert np.array_equal(ha[ok], agg[ok])
+
+
+@pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
+def test_typed_input_twin(L, vi, kind):
+    """jjs_verify_ext stages on the CPU twin: typed items built from wire items give the wire result; typed-only
+    failure modes (z = 0, inconsistent t1 t2, off-curve, unreduced limbs, projective identity) match the oracle."""
+    from tests import typed_inputs as ti
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    n = 150
+    pk, sig, msg = gen(0x7E, n)
+    pk, sig, msg, _, _ = adv.make_adversarial(kind, pk, sig, msg, seed=3, frac=0.5)
+    st_wire, c_wire = ver(pk, sig, msg)
+    pts, u, keep = ti.to_typed(vi, pk, sig, msg, seed=4)
+    pts, u, msg_k, st_wire, c_wire = pts[keep], u[keep], msg[keep], st_wire[keep], c_wire[keep]
+    m = int(keep.sum())
+    st_o, c_o = co.verify_ext(vi, pts, u, msg_k)
+    assert np.array_equal(st_o, st_wire) and np.array_equal(c_o, c_wire)     # oracle: typed == wire
+    hst, hc = np.zeros(m, np.uint8), np.zeros((m, 32), np.uint8)
+    L.hs_verify_ext(vi, _p(pts), _p(u), _p(msg_k), C.c_size_t(m), _p(hst), _p(hc))
+    assert np.array_equal(hst, st_o) and np.array_equal(hc, c_o)
+    bad, expected = ti.corrupt_typed(pts, st_o, seed=5)
+    st_b, c_b = co.verify_ext(vi, bad, u, msg_k)
+    L.hs_verify_ext(vi, _p(bad), _p(u), _p(msg_k), C.c_size_t(m), _p(hst), _p(hc))
+    assert np.array_equal(hst, st_b) and np.array_equal(hc, c_b)
+    for i, e in enumerate(expected):
+        if e is not None and st_o[i] != 3:
+            assert st_b[i] == e, (i, e, st_b[i])
