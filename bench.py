@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -55,34 +54,34 @@ def int32_peak():
 
 
 class ClockSampler:
+    """nvidia-smi streaming every 100 ms during the timed region (B200_PROFILING.md, clocks line)."""
     QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
-
-    def _run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.index, self.proc = index, None
 
     def start(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        time.sleep(0.25)  # let the first samples land inside the timed region
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=6)
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        samples = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            samples = [[x.strip() for x in line.split(",")] for line in out.splitlines() if line.strip()]
+        sm = sorted(int(s[0]) for s in samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in samples if len(s) > 1 and s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for s in samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
