@@ -41,6 +41,9 @@ extern "C" {
 #define JJS_INVALID_SIGNATURE 1
 #define JJS_INVALID_POINT 2
 #define JJS_BYTES_ERROR 3
+/* multisig::combine only */
+#define JJS_INVALID_MULTISIG_TRANSCRIPT 4
+#define JJS_INVALID_MULTISIG_SHARE 5
 
 /* call return codes */
 #define JJS_SUCCESS 0
@@ -111,6 +114,18 @@ int jjs_verify_ext(jjs_ctx* ctx, int variant, const uint8_t* points_ext160, cons
 /* Test-data utility for the typed path: wire point i -> the 160-byte coordinates (u z, v z, z, u z, v) with the caller's
  * Montgomery value z (z_mont32, any non-zero reduced field element); zeros if the point does not decode.  Host buffers. */
 int jjs_points_to_ext(jjs_ctx* ctx, const uint8_t* points32, const uint8_t* z_mont32, size_t n, uint8_t* out160);
+
+/* multisig::combine for n sessions (reference src/multisig.rs:311-347; the share check is verify_share,
+ * src/multisig.rs:255-281, 366-387).  Session i owns participants offsets[i] .. offsets[i+1]-1 of the ragged arrays
+ * pks32 (PublicKey::to_bytes), R32 / S32 (compressed commitment points) and z32 (JubJubScalar::to_bytes shares);
+ * msg32 has one BlsScalar per session; at most 31 participants per session.  Per session:
+ *   status 0: Ok(Signature), sig64 = (sum z_i) || RSa       5: Err(InvalidMultisigShare(bad_index))
+ *          3: some field fails from_bytes                     4: Err(InvalidMultisigTranscript) (no participants)
+ * share_ok (one byte per participant) is what verify_share returns for every participant, not only the first bad
+ * one.  Like the reference, no subgroup validation is applied to any point.  Host buffers, device 0. */
+int jjs_multisig_combine(jjs_ctx* ctx, const uint8_t* pks32, const uint8_t* R32, const uint8_t* S32, const uint8_t* z32,
+                         const uint32_t* offsets, const uint8_t* msg32, size_t n, uint8_t* share_ok_or_null, uint8_t* status,
+                         uint32_t* bad_index_or_null, uint8_t* sig64_or_null);
 
 /* Challenge hash only (hash parity hook): c = challenge_hash(..) for already-valid encodings, no curve
  * check.  variant: 0 single, 1 double, 2 var-generator.  Host buffers. */

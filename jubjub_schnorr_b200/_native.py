@@ -15,7 +15,7 @@ EXPORTS = [
     "jjs_init", "jjs_destroy", "jjs_last_error", "jjs_device_count", "jjs_launch_count",
     "jjs_verify_single", "jjs_verify_double", "jjs_verify_vargen", "jjs_verify_aggregate",
     "jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device",
-    "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect", "jjs_subgroup_check", "jjs_verify_aggregate_device", "jjs_sign_aggregate_batch", "jjs_verify_ext", "jjs_points_to_ext",
+    "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect", "jjs_subgroup_check", "jjs_verify_aggregate_device", "jjs_sign_aggregate_batch", "jjs_verify_ext", "jjs_points_to_ext", "jjs_multisig_combine",
 ]
 
 _lib = None
@@ -73,5 +73,7 @@ def lib():
     L.jjs_verify_ext.restype = C.c_int
     L.jjs_points_to_ext.argtypes = [vp, vp, vp, sz, vp]
     L.jjs_points_to_ext.restype = C.c_int
+    L.jjs_multisig_combine.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.jjs_multisig_combine.restype = C.c_int
     _lib = L
     return L

@@ -138,6 +138,22 @@ class BatchVerifier:
         self._check(self._lib.jjs_points_to_ext(self._ctx, pts.ctypes.data, z.ctypes.data, pts.shape[0], out.ctypes.data), "jjs_points_to_ext")
         return out
 
+    def multisig_combine(self, pks32, R32, S32, z32, offsets, msg32):
+        """multisig::combine per session: (status[n], bad_index[n], sig[n,64], share_ok[K]); see jjs_multisig_combine."""
+        pks, Rs, Ss, zs, msg = _u8(pks32, 32, "pks"), _u8(R32, 32, "R"), _u8(S32, 32, "S"), _u8(z32, 32, "z"), _u8(msg32, 32, "msg")
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n, K = msg.shape[0], pks.shape[0]
+        if offsets.shape[0] != n + 1 or int(offsets[0]) != 0 or int(offsets[-1]) != K or not (Rs.shape[0] == Ss.shape[0] == zs.shape[0] == K):
+            raise ValueError("offsets must have n + 1 entries covering the participant arrays exactly")
+        status = np.empty(n, dtype=np.uint8)
+        bad = np.empty(n, dtype=np.uint32)
+        sig = np.empty((n, 64), dtype=np.uint8)
+        ok = np.empty(K, dtype=np.uint8)
+        self._check(self._lib.jjs_multisig_combine(self._ctx, pks.ctypes.data, Rs.ctypes.data, Ss.ctypes.data, zs.ctypes.data, offsets.ctypes.data,
+                                                   msg.ctypes.data, n, ok.ctypes.data, status.ctypes.data, bad.ctypes.data, sig.ctypes.data),
+                    "jjs_multisig_combine")
+        return status, bad, sig, ok
+
     def challenge_only(self, variant, pk, sig, msg32):
         pk, sig, msg = _u8(pk, PK_SIZE[variant], "pk"), _u8(sig, SIG_SIZE[variant], "sig"), _u8(msg32, 32, "msg")
         n = msg.shape[0]

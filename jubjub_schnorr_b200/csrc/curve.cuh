@@ -384,10 +384,9 @@ JJS_HD void pniels_load(pniels& n, const fq* tab, size_t stride, int entry) {
     n.z2 = p[2 * stride];
     n.t2d = p[3 * stride];
 }
-JJS_HD void varbase_table_build(fq* tab, size_t stride, const fq& u, const fq& v) {
-    ext p, acc;
+JJS_HD void varbase_table_build_ext(fq* tab, size_t stride, const ext& p) {
+    ext acc;
     pniels n1, n;
-    ext_from_affine(p, u, v);
     pniels_identity(n);
     pniels_store(tab, stride, 0, n);
     ext_to_pniels(n1, p);
@@ -401,6 +400,11 @@ JJS_HD void varbase_table_build(fq* tab, size_t stride, const fq& u, const fq& v
         ext_to_pniels(n, acc);
         pniels_store(tab, stride, k, n);
     }
+}
+JJS_HD void varbase_table_build(fq* tab, size_t stride, const fq& u, const fq& v) {
+    ext p;
+    ext_from_affine(p, u, v);
+    varbase_table_build_ext(tab, stride, p);
 }
 // acc = 16 * acc + digit * P, digit in [-8, 8], P's multiples in `tab`
 template <bool WANT_T>

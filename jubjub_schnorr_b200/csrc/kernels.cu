@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/jjschnorr_b200.h"
+#include "multisig_core.cuh"
 #include "sign_core.cuh"
 #include "verify_core.cuh"
 
@@ -189,6 +190,46 @@ __global__ void __launch_bounds__(BLOCK) k_sign(const uint8_t* sk, const uint8_t
     for (int k = 0; k < PKW / 4; k++) po[k] = ok ? make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < SGW / 4; k++) so[k] = ok ? make_uint4(sig[4 * k], sig[4 * k + 1], sig[4 * k + 2], sig[4 * k + 3]) : make_uint4(0, 0, 0, 0);
+}
+
+// ---- multisig::combine ---------------------------------------------------------------------------------------------
+struct MsigBuffers {
+    fq *pu, *pv;           // [3K] decoded pk | R | S
+    uint8_t* pf;           // [3K]
+    uint32_t *d_words, *cd_words;  // [K][8]
+    uint32_t* a_words;     // [n][8]
+    fq *rsa_u, *rsa_v;     // [n]
+    uint8_t* sflags;       // [n]
+    uint8_t* share_ok;     // [K]
+    const uint32_t *offsets, *owner, *order;
+};
+
+__global__ void __launch_bounds__(BLOCK) k_msig_session(MsigBuffers b, size_t K, size_t n, WireField msg, WireField zf, fq* tab, size_t stride) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    size_t s = b.order[t];
+    stage_msig_session(b.pu, b.pv, b.pf, K, b.offsets[s], b.offsets[s + 1], msg, zf, s, b.d_words, b.cd_words, b.a_words, b.rsa_u, b.rsa_v, b.sflags,
+                       tab + t, tab + 36 * stride + t, stride);
+}
+__global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_msig_share(MsigBuffers b, size_t K, WireField zf, fq* tab, size_t stride, Tables T) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    size_t s = b.owner[j];
+    bool ok = false;
+    if (b.sflags[s] == (SF_DECODED | SF_NONEMPTY))
+        ok = stage_msig_share(b.pu, b.pv, K, j, zf, b.cd_words, b.a_words + 8 * s, T.fb_g, tab + j, tab + 36 * stride + j, stride);
+    b.share_ok[j] = ok ? 1 : 0;
+}
+__global__ void __launch_bounds__(BLOCK) k_msig_finalize(MsigBuffers b, size_t n, WireField zf, uint8_t* status, uint32_t* bad, uint8_t* sig64) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t sig[16], bi;
+    uint8_t st = stage_msig_finalize(b.sflags, b.share_ok, b.offsets[s], b.offsets[s + 1], s, zf, b.rsa_u, b.rsa_v, &bi, sig);
+    status[s] = st;
+    bad[s] = bi;
+    uint4* o = reinterpret_cast<uint4*>(sig64 + 64 * s);
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = make_uint4(sig[4 * k], sig[4 * k + 1], sig[4 * k + 2], sig[4 * k + 3]);
 }
 
 // Aggregate-key items for synthetic batches: signer keys pk_j = sk_j * G, the aggregate secret sum_j d_j sk_j with the
@@ -642,6 +683,94 @@ int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, c
     return rc;
 }
 
+// multisig::combine for n ragged sessions (host buffers, device 0); chunks hold at most 2^20 participants
+int run_msig(jjs_ctx* ctx, const uint8_t* pks, const uint8_t* Rs, const uint8_t* Ss, const uint8_t* zs, const uint32_t* offsets, const uint8_t* msg,
+             size_t n, uint8_t* share_ok, uint8_t* status, uint32_t* bad, uint8_t* sig) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (n == 0) return JJS_SUCCESS;
+    if (!offsets || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    if (offsets[0] != 0) return fail(ctx, JJS_ERR_ARGUMENT, "offsets[0] must be 0");
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, JJS_ERR_ARGUMENT, "offsets must be non-decreasing");
+    if (offsets[n] && (!pks || !Rs || !Ss || !zs)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    DeviceState& d = ctx->dev[0];
+    int rc = ensure_scratch(ctx, d);
+    if (rc) return rc;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    Tables T = d.tables();
+    std::vector<uint32_t> rel, owner, order;
+    for (size_t s0 = 0; s0 < n;) {
+        size_t s1 = s0;
+        while (s1 < n && s1 - s0 < CHUNK_ITEMS && offsets[s1 + 1] - offsets[s0] <= TAB_THREADS) s1++;
+        if (s1 == s0) return fail(ctx, JJS_ERR_ARGUMENT, "a session has more than 2^20 participants");
+        const size_t m = s1 - s0, K = offsets[s1] - offsets[s0], k0 = offsets[s0];
+        rel.resize(m + 1);
+        owner.resize(K ? K : 1);
+        order.resize(m);
+        size_t hist[34] = {0};
+        for (size_t i = 0; i <= m; i++) rel[i] = offsets[s0 + i] - (uint32_t)k0;
+        for (size_t i = 0; i < m; i++) {
+            uint32_t c = rel[i + 1] - rel[i];
+            for (uint32_t j = rel[i]; j < rel[i + 1]; j++) owner[j] = (uint32_t)i;
+            hist[(c > 32 ? 32 : c) + 1]++;
+        }
+        for (int b = 0; b < 33; b++) hist[b + 1] += hist[b];
+        for (size_t i = 0; i < m; i++) {
+            uint32_t c = rel[i + 1] - rel[i];
+            order[hist[c > 32 ? 32 : c]++] = (uint32_t)i;
+        }
+        // one device buffer: wire inputs | decoded points | scalars | results | index arrays
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
+        size_t o_pk = take(32 * K), o_R = take(32 * K), o_S = take(32 * K), o_z = take(32 * K), o_msg = take(32 * m), o_pu = take(sizeof(fq) * 3 * K),
+               o_pv = take(sizeof(fq) * 3 * K), o_pf = take(3 * K), o_d = take(32 * K), o_cd = take(32 * K), o_a = take(32 * m), o_ru = take(sizeof(fq) * m),
+               o_rv = take(sizeof(fq) * m), o_sf = take(m), o_ok = take(K), o_off = take(4 * (m + 1)), o_own = take(4 * K), o_ord = take(4 * m),
+               o_st = take(m), o_bad = take(4 * m), o_sig = take(64 * m);
+        if (o > d.agg_stage_bytes) {
+            cudaStreamSynchronize(d.stream);
+            cudaFree(d.agg_stage);
+            d.agg_stage = nullptr;
+            d.agg_stage_bytes = 0;
+            JJS_CUDA(ctx, cudaMalloc(&d.agg_stage, o));
+            d.agg_stage_bytes = o;
+        }
+        uint8_t* B = d.agg_stage;
+        cudaStream_t st = d.stream;
+        if (K) {
+            cudaMemcpyAsync(B + o_pk, pks + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(B + o_R, Rs + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(B + o_S, Ss + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(B + o_z, zs + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(B + o_own, owner.data(), 4 * K, cudaMemcpyHostToDevice, st);
+        }
+        cudaMemcpyAsync(B + o_msg, msg + 32 * s0, 32 * m, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(B + o_off, rel.data(), 4 * (m + 1), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(B + o_ord, order.data(), 4 * m, cudaMemcpyHostToDevice, st);
+        MsigBuffers b;
+        b.pu = reinterpret_cast<fq*>(B + o_pu); b.pv = reinterpret_cast<fq*>(B + o_pv); b.pf = B + o_pf;
+        b.d_words = reinterpret_cast<uint32_t*>(B + o_d); b.cd_words = reinterpret_cast<uint32_t*>(B + o_cd); b.a_words = reinterpret_cast<uint32_t*>(B + o_a);
+        b.rsa_u = reinterpret_cast<fq*>(B + o_ru); b.rsa_v = reinterpret_cast<fq*>(B + o_rv); b.sflags = B + o_sf; b.share_ok = B + o_ok;
+        b.offsets = reinterpret_cast<uint32_t*>(B + o_off); b.owner = reinterpret_cast<uint32_t*>(B + o_own); b.order = reinterpret_cast<uint32_t*>(B + o_ord);
+        Fields f;
+        f.f[0] = WireField{B + o_pk, 32}; f.f[1] = WireField{B + o_R, 32}; f.f[2] = WireField{B + o_S, 32}; f.f[3] = WireField{nullptr, 0};
+        WireField fmsg{B + o_msg, 32}, fz{B + o_z, 32};
+        if (K) k_decode<<<blocks_for(3 * K), BLOCK, 0, st>>>(f, 3, 0, K, b.pu, b.pv, b.pf, T, false);
+        k_msig_session<<<blocks_for(m), BLOCK, 0, st>>>(b, K, m, fmsg, fz, d.tab, TAB_THREADS);
+        if (K) k_msig_share<<<blocks_for(K), BLOCK, 0, st>>>(b, K, fz, d.tab, TAB_THREADS, T);
+        k_msig_finalize<<<blocks_for(m), BLOCK, 0, st>>>(b, m, fz, B + o_st, reinterpret_cast<uint32_t*>(B + o_bad), B + o_sig);
+        ctx->launches += 4;
+        cudaMemcpyAsync(status + s0, B + o_st, m, cudaMemcpyDeviceToHost, st);
+        if (bad) cudaMemcpyAsync(bad + s0, B + o_bad, 4 * m, cudaMemcpyDeviceToHost, st);
+        if (sig) cudaMemcpyAsync(sig + 64 * s0, B + o_sig, 64 * m, cudaMemcpyDeviceToHost, st);
+        if (share_ok && K) cudaMemcpyAsync(share_ok + k0, B + o_ok, K, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "multisig combine failed: %s", cudaGetErrorString(e));
+        s0 = s1;
+    }
+    return JJS_SUCCESS;
+}
+
 int run_sign(jjs_ctx* ctx, int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, size_t n, uint8_t* pk_out,
              uint8_t* sig_out) {
     if (!ctx) return JJS_ERR_ARGUMENT;
@@ -885,6 +1014,11 @@ JJS_API int jjs_points_to_ext(jjs_ctx* ctx, const uint8_t* points32, const uint8
     cudaFree(b);
     if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "points_to_ext failed: %s", cudaGetErrorString(e));
     return JJS_SUCCESS;
+}
+JJS_API int jjs_multisig_combine(jjs_ctx* ctx, const uint8_t* pks32, const uint8_t* R32, const uint8_t* S32, const uint8_t* z32, const uint32_t* offsets,
+                                 const uint8_t* msg32, size_t n, uint8_t* share_ok_or_null, uint8_t* status, uint32_t* bad_index_or_null,
+                                 uint8_t* sig64_or_null) {
+    return run_msig(ctx, pks32, R32, S32, z32, offsets, msg32, n, share_ok_or_null, status, bad_index_or_null, sig64_or_null);
 }
 JJS_API void jjs_profile_enable(jjs_ctx* ctx, int on) {
     if (ctx) ctx->profile = on != 0;

@@ -224,7 +224,7 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
 // d_j = H_trunc(pk_j || pk_0 .. pk_{n-1}),  agg = sum_j d_j * pk_j.  Like the reference, the signer keys are NOT
 // validated (only decoded); the aggregate is then treated exactly as the PublicKey of a single verification: its
 // affine coordinates, validity flags (identity, torsion freeness) and wire encoding are written to slot `out_index`.
-JJS_HD void aggregate_coeff(int8_t* digits, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j) {
+JJS_HD void aggregate_coeff_words(uint32_t* d, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j) {
     Sponge sp;
     sponge_start(sp, (int)(2 + 2 * (hi - lo)));
     sponge_absorb(sp, keys_u[j]);
@@ -234,8 +234,11 @@ JJS_HD void aggregate_coeff(int8_t* digits, const fq* keys_u, const fq* keys_v, 
         sponge_absorb(sp, keys_u[k]);
         sponge_absorb(sp, keys_v[k]);
     }
-    uint32_t d[8];
     sponge_squeeze_truncated(d, sp);
+}
+JJS_HD void aggregate_coeff(int8_t* digits, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j) {
+    uint32_t d[8];
+    aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
     recode_signed16(digits, d);
 }
 

@@ -125,6 +125,39 @@ def gen_aggregate(seed, signers, first=0, threads=0):
     return pks, offsets, sig, msg
 
 
+def multisig_combine(pks, Rs, Ss, zs, offsets, msg, threads=0):
+    """multisig::combine over ragged sessions.  Returns (status[n], bad_index[n], sig[n,64], share_ok[K])."""
+    pks, Rs, Ss, zs, msg = _u8(pks, 32), _u8(Rs, 32), _u8(Ss, 32), _u8(zs, 32), _u8(msg, 32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    n, K = msg.shape[0], pks.shape[0]
+    assert offsets.shape[0] == n + 1 and int(offsets[-1]) == K == Rs.shape[0] == Ss.shape[0] == zs.shape[0]
+    status = np.zeros(n, dtype=np.uint8)
+    bad = np.zeros(n, dtype=np.uint32)
+    sig = np.zeros((n, 64), dtype=np.uint8)
+    ok = np.zeros(K, dtype=np.uint8)
+    f = lib().jjo_multisig_combine
+    f.argtypes = [C.c_void_p] * 6 + [C.c_size_t] + [C.c_void_p] * 4 + [C.c_int]
+    f.restype = None
+    f(_p(pks), _p(Rs), _p(Ss), _p(zs), _p(offsets), _p(msg), n, _p(ok), _p(status), _p(bad), _p(sig), threads or default_threads())
+    return status, bad, sig, ok
+
+
+def gen_multisig(seed, signers, first=0, threads=0):
+    """Valid SpeedyMuSig sessions.  Returns (pks, Rs, Ss, zs [K,32 each], offsets[n+1], msg[n,32])."""
+    signers = np.asarray(signers, dtype=np.uint32)
+    n = signers.shape[0]
+    offsets = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(signers, out=offsets[1:])
+    K = int(offsets[-1])
+    pks, Rs, Ss, zs = (np.zeros((K, 32), dtype=np.uint8) for _ in range(4))
+    msg = np.zeros((n, 32), dtype=np.uint8)
+    f = lib().jjo_gen_multisig
+    f.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t] + [C.c_void_p] * 6 + [C.c_int]
+    f.restype = None
+    f(seed, first, n, _p(offsets), _p(pks), _p(Rs), _p(Ss), _p(zs), _p(msg), threads or default_threads())
+    return pks, Rs, Ss, zs, offsets, msg
+
+
 def verify_ext(variant, pts160, u32, msg32):
     """Typed inputs (JubJubExtended Montgomery coordinates, 160 bytes per point, item-major); single-threaded."""
     slots = {0: 2, 1: 4, 2: 3}[variant]

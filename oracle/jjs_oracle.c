@@ -715,12 +715,127 @@ static void gen_aggregate(uint64_t seed, uint64_t idx, int n, uint8_t *pks32, ui
     free(sk); free(pre);
 }
 
+/* ------------------------------------------------------------------ multisig: combine / verify_share */
+enum { ST_INVALID_MULTISIG_TRANSCRIPT = 4, ST_INVALID_MULTISIG_SHARE = 5 };
+typedef struct { fe *d; pt agg; fe agg_u, agg_v; fe a; pt RSa; fe c; } msig_coeffs;
+
+/* multisig_common (reference src/multisig.rs:440-500); d must hold n elements (Fr Montgomery) */
+static void msig_common(msig_coeffs *k, const pt *pks, const pt *Rs, const pt *Ss, int n, const fe *m) {
+    fe *pre = (fe *)malloc(sizeof(fe) * (size_t)(3 + 4 * n + 2));
+    for (int i = 0; i < n; i++) pt_to_affine(&pre[2 + 2 * i], &pre[3 + 2 * i], &pks[i]);
+    pt acc, t;
+    pt_identity(&acc);
+    for (int i = 0; i < n; i++) {
+        pre[0] = pre[2 + 2 * i];
+        pre[1] = pre[3 + 2 * i];
+        poseidon_hash_truncated(&k->d[i], NULL, pre, 2 + 2 * n);
+        pt_mul(&t, &pks[i], &k->d[i]);
+        pt_add(&acc, &acc, &t);
+    }
+    k->agg = acc;
+    pt_to_affine(&k->agg_u, &k->agg_v, &acc);
+    pre[0] = k->agg_u; pre[1] = k->agg_v; pre[2] = *m;
+    for (int i = 0; i < n; i++) {
+        pt_to_affine(&pre[3 + 4 * i], &pre[4 + 4 * i], &Rs[i]);
+        pt_to_affine(&pre[5 + 4 * i], &pre[6 + 4 * i], &Ss[i]);
+    }
+    poseidon_hash_truncated(&k->a, NULL, pre, 3 + 4 * n);
+    pt_identity(&acc);
+    for (int i = 0; i < n; i++) {
+        pt_add(&acc, &acc, &Rs[i]);
+        pt_mul(&t, &Ss[i], &k->a);
+        pt_add(&acc, &acc, &t);
+    }
+    k->RSa = acc;
+    fe in[5];
+    pt_to_affine(&in[0], &in[1], &acc);
+    in[2] = k->agg_u; in[3] = k->agg_v; in[4] = *m;
+    poseidon_hash_truncated(&k->c, NULL, in, 5);
+    free(pre);
+}
+/* combine (reference src/multisig.rs:311-347) on wire encodings */
+static int msig_combine_one(const uint8_t *pks32, const uint8_t *R32, const uint8_t *S32, const uint8_t *z32, int n, const uint8_t msg32[32],
+                            uint8_t *share_ok, uint32_t *bad, uint8_t sig64[64]) {
+    *bad = 0xffffffffu;
+    memset(sig64, 0, 64);
+    for (int i = 0; i < n; i++) share_ok[i] = 0;
+    if (n <= 0) return ST_INVALID_MULTISIG_TRANSCRIPT;
+    if (3 + 4 * n > JJO_MAX_ABSORB) return ST_INVALID_MULTISIG_TRANSCRIPT;
+    pt *P = (pt *)malloc(sizeof(pt) * 3 * (size_t)n);
+    fe *z = (fe *)malloc(sizeof(fe) * 2 * (size_t)n), m;
+    pt *pks = P, *Rs = P + n, *Ss = P + 2 * n;
+    int ok = f_from_bytes(&FQ, &m, msg32);
+    for (int i = 0; i < n; i++) {
+        ok &= pt_decode(&pks[i], pks32 + 32 * i);
+        ok &= pt_decode(&Rs[i], R32 + 32 * i);
+        ok &= pt_decode(&Ss[i], S32 + 32 * i);
+        ok &= f_from_bytes(&FR, &z[i], z32 + 32 * i);
+    }
+    int st = ST_BYTES_ERROR;
+    if (ok) {
+        msig_coeffs k;
+        k.d = z + n;
+        msig_common(&k, pks, Rs, Ss, n, &m);
+        fe sum;
+        f_zero(&sum);
+        st = ST_OK;
+        for (int i = 0; i < n; i++) {
+            fe cd;
+            pt a, b, lhs, rhs;
+            f_mul(&FR, &cd, &k.c, &k.d[i]);
+            pt_mul(&a, &G_PT, &z[i]); pt_mul(&b, &pks[i], &cd); pt_add(&lhs, &a, &b);
+            pt_mul(&a, &Ss[i], &k.a); pt_add(&rhs, &Rs[i], &a);
+            share_ok[i] = (uint8_t)pt_eq(&lhs, &rhs);
+            if (!share_ok[i] && st == ST_OK) { st = ST_INVALID_MULTISIG_SHARE; *bad = (uint32_t)i; }
+            f_add(&FR, &sum, &sum, &z[i]);
+        }
+        if (st == ST_OK) {
+            f_to_bytes(&FR, sig64, &sum);
+            pt_encode(sig64 + 32, &k.RSa);
+        }
+    }
+    free(P); free(z);
+    return st;
+}
+/* a complete, valid session: keys, commitments R_i = r_i G, S_i = s_i G and shares z_i = r_i + a s_i - c d_i sk_i
+ * (sign_round_1 / sign_round_2, reference src/multisig.rs:172-253) */
+static void gen_multisig(uint64_t seed, uint64_t idx, int n, uint8_t *pks32, uint8_t *R32, uint8_t *S32, uint8_t *z32, uint8_t msg32[32]) {
+    uint64_t st;
+    uint8_t w[64];
+    item_rng(&st, seed, idx, 5);
+    fe *sc = (fe *)malloc(sizeof(fe) * 4 * (size_t)n), m;
+    pt *P = (pt *)malloc(sizeof(pt) * 3 * (size_t)n);
+    fe *sk = sc, *r = sc + n, *s = sc + 2 * n;
+    for (int i = 0; i < n; i++) {
+        rand_wide(&st, w); f_from_wide(&FR, &sk[i], w);
+        rand_wide(&st, w); f_from_wide(&FR, &r[i], w);
+        rand_wide(&st, w); f_from_wide(&FR, &s[i], w);
+        fb_mul(&P[i], &FB_G, &sk[i]); fb_mul(&P[n + i], &FB_G, &r[i]); fb_mul(&P[2 * n + i], &FB_G, &s[i]);
+        pt_encode(pks32 + 32 * i, &P[i]); pt_encode(R32 + 32 * i, &P[n + i]); pt_encode(S32 + 32 * i, &P[2 * n + i]);
+    }
+    rand_wide(&st, w); f_from_wide(&FQ, &m, w);
+    f_to_bytes(&FQ, msg32, &m);
+    msig_coeffs k;
+    k.d = sc + 3 * n;
+    msig_common(&k, P, P + n, P + 2 * n, n, &m);
+    for (int i = 0; i < n; i++) {
+        fe t, zz;
+        f_mul(&FR, &t, &k.a, &s[i]); f_add(&FR, &zz, &r[i], &t);
+        f_mul(&FR, &t, &k.c, &k.d[i]); f_mul(&FR, &t, &t, &sk[i]); f_sub(&FR, &zz, &zz, &t);
+        f_to_bytes(&FR, z32 + 32 * i, &zz);
+    }
+    free(sc); free(P);
+}
+
 /* ------------------------------------------------------------------ threaded batch drivers */
 typedef struct {
     int kind; /* 0 verify single, 1 double, 2 vargen, 3 aggregate; 10.. generate */
     const uint8_t *pk, *sig, *msg;
     uint8_t *opk, *osig, *omsg;
     const uint32_t *offsets;
+    const uint8_t *R, *S, *z;
+    uint8_t *oR, *oS, *oz, *share_ok;
+    uint32_t *bad;
     uint8_t *status, *c, *agg;
     uint64_t seed, first;
     size_t lo, hi;
@@ -738,6 +853,19 @@ static void *worker(void *arg) {
             j->status[i] = (uint8_t)verify_aggregate_one(j->pk + 32 * (size_t)j->offsets[i], (int)(j->offsets[i + 1] - j->offsets[i]),
                                                          j->sig + 64 * i, j->msg + 32 * i, c, j->agg ? j->agg + 32 * i : NULL);
             break;
+        case 4: {
+            size_t lo = j->offsets[i];
+            int cnt = (int)(j->offsets[i + 1] - j->offsets[i]);
+            j->status[i] = (uint8_t)msig_combine_one(j->pk + 32 * lo, j->R + 32 * lo, j->S + 32 * lo, j->z + 32 * lo, cnt, j->msg + 32 * i,
+                                                     j->share_ok + lo, &j->bad[i], j->osig + 64 * i);
+            break;
+        }
+        case 14: {
+            size_t lo = j->offsets[i];
+            gen_multisig(j->seed, j->first + i, (int)(j->offsets[i + 1] - j->offsets[i]), j->opk + 32 * lo, j->oR + 32 * lo, j->oS + 32 * lo,
+                         j->oz + 32 * lo, j->omsg + 32 * i);
+            break;
+        }
         case 10: gen_single(j->seed, j->first + i, j->opk + 32 * i, j->osig + 64 * i, j->omsg + 32 * i); break;
         case 11: gen_double(j->seed, j->first + i, j->opk + 64 * i, j->osig + 96 * i, j->omsg + 32 * i); break;
         case 12: gen_vargen(j->seed, j->first + i, j->opk + 64 * i, j->osig + 64 * i, j->omsg + 32 * i); break;
@@ -829,6 +957,18 @@ EXPORT int jjo_point_to_ext(const uint8_t in32[32], const uint8_t z_mont32[32], 
     c[3] = c[0]; c[4] = p.Y;
     for (int k = 0; k < 5; k++) memcpy(out160 + 32 * k, c[k].l, 32);
     return 1;
+}
+
+EXPORT void jjo_multisig_combine(const uint8_t *pks32, const uint8_t *R32, const uint8_t *S32, const uint8_t *z32, const uint32_t *offsets,
+                                 const uint8_t *msg32, size_t n, uint8_t *share_ok, uint8_t *status, uint32_t *bad_index, uint8_t *sig64, int threads) {
+    job j = {0}; j.kind = 4; j.pk = pks32; j.R = R32; j.S = S32; j.z = z32; j.offsets = offsets; j.msg = msg32; j.share_ok = share_ok;
+    j.status = status; j.bad = bad_index; j.osig = sig64;
+    run(&j, n, threads);
+}
+EXPORT void jjo_gen_multisig(uint64_t seed, uint64_t first, size_t n, const uint32_t *offsets, uint8_t *pks32, uint8_t *R32, uint8_t *S32,
+                             uint8_t *z32, uint8_t *msg32, int threads) {
+    job j = {0}; j.kind = 14; j.seed = seed; j.first = first; j.offsets = offsets; j.opk = pks32; j.oR = R32; j.oS = S32; j.oz = z32; j.omsg = msg32;
+    run(&j, n, threads);
 }
 
 /* small helpers for building adversarial inputs and for unit parity checks */

@@ -456,3 +456,52 @@ def b58decode(s: str, length: int) -> bytes:
     for ch in s:
         n = n * 58 + _B58.index(ch)
     return n.to_bytes(length, "big")
+
+
+# --------------------------------------------------------------------------------------------
+# multisig: share verification and combine
+# --------------------------------------------------------------------------------------------
+STATUS_INVALID_MULTISIG_TRANSCRIPT = 4  # Error::InvalidMultisigTranscript  (src/error.rs)
+STATUS_INVALID_MULTISIG_SHARE = 5       # Error::InvalidMultisigShare(index)
+
+
+def multisig_common(pks, Rs, Ss, m):
+    """multisig::multisig_common (src/multisig.rs:440-500): (d_i list, aggregate key, a, RSa, c)."""
+    ds = [delinearization_coeff(p, pks) for p in pks]
+    agg = IDENTITY
+    for p, d in zip(pks, ds):
+        agg = padd(agg, pmul(p, d))
+    pre = [agg[0], agg[1], m]
+    for R, S in zip(Rs, Ss):
+        pre += [R[0], R[1], S[0], S[1]]
+    a = poseidon_hash_truncated(pre)
+    RSa = IDENTITY
+    for R, S in zip(Rs, Ss):
+        RSa = padd(padd(RSa, R), pmul(S, a))
+    c = challenge_single(RSa, agg, m)
+    return ds, agg, a, RSa, c
+
+
+def multisig_share_ok(z, i, pks, Rs, Ss, coeffs) -> bool:
+    """verify_share_with_coefficients (src/multisig.rs:366-387): z_i G + (c d_i) pk_i == R_i + a S_i."""
+    ds, _, a, _, c = coeffs
+    lhs = padd(pmul(G, z), pmul(pks[i], c * ds[i] % R_ORDER))
+    return lhs == padd(Rs[i], pmul(Ss[i], a))
+
+
+def multisig_combine(zs32, pks32, Rs32, Ss32, msg32):
+    """multisig::combine (src/multisig.rs:311-347) on wire encodings.
+    Returns (status, first_bad_index or None, signature bytes or None, [share_ok])."""
+    n = len(pks32)
+    if n == 0 or not (len(zs32) == len(Rs32) == len(Ss32) == n):
+        return STATUS_INVALID_MULTISIG_TRANSCRIPT, None, None, []
+    zs = [fr_from_le(z) for z in zs32]
+    pks, Rs, Ss = ([point_from_bytes(b) for b in arr] for arr in (pks32, Rs32, Ss32))
+    m = fq_from_le(msg32)
+    if None in zs or None in pks or None in Rs or None in Ss or m is None:
+        return STATUS_BYTES_ERROR, None, None, []
+    coeffs = multisig_common(pks, Rs, Ss, m)
+    oks = [multisig_share_ok(zs[i], i, pks, Rs, Ss, coeffs) for i in range(n)]
+    if not all(oks):
+        return STATUS_INVALID_MULTISIG_SHARE, oks.index(False), None, oks
+    return STATUS_OK, None, le32(sum(zs) % R_ORDER) + point_to_bytes(coeffs[3]), oks

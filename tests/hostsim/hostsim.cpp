@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../jubjub_schnorr_b200/csrc/multisig_core.cuh"
 #include "../../jubjub_schnorr_b200/csrc/sign_core.cuh"
 #include "../../jubjub_schnorr_b200/csrc/verify_core.cuh"
 namespace tables {
@@ -212,6 +213,30 @@ void hs_verify_ext(int variant, const uint8_t* pts, const uint8_t* u32, const ui
         }
         status[i] = stage_status(variant, pf.data(), itf[i], n, i);
         if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
+    }
+}
+// multisig::combine through the stage functions
+void hs_multisig_combine(const uint8_t* pks, const uint8_t* Rs, const uint8_t* Ss, const uint8_t* zs, const uint32_t* offsets, const uint8_t* msg, size_t n,
+                         uint8_t* share_ok, uint8_t* status, uint32_t* bad, uint8_t* sig) {
+    ensure_ready();
+    size_t K = offsets[n];
+    std::vector<fq> pu(3 * K + 1), pv(3 * K + 1), tab(72), ru(n), rv(n);
+    std::vector<uint8_t> pf(3 * K + 1), sf(n);
+    std::vector<uint32_t> dw(8 * K + 8), cdw(8 * K + 8), aw(8 * n);
+    WireField f[3] = {{pks, 32}, {Rs, 32}, {Ss, 32}}, fmsg{msg, 32}, fz{zs, 32};
+    for (int s = 0; s < 3; s++)
+        for (size_t j = 0; j < K; j++) stage_decode(f[s], j, pu.data(), pv.data(), pf.data(), s * K + j, g_tables, false);
+    for (size_t s = 0; s < n; s++)
+        stage_msig_session(pu.data(), pv.data(), pf.data(), K, offsets[s], offsets[s + 1], fmsg, fz, s, dw.data(), cdw.data(), aw.data(), ru.data(), rv.data(),
+                           sf.data(), tab.data(), tab.data() + 36, 1);
+    for (size_t s = 0; s < n; s++)
+        for (uint32_t j = offsets[s]; j < offsets[s + 1]; j++)
+            share_ok[j] = sf[s] == (SF_DECODED | SF_NONEMPTY) &&
+                          stage_msig_share(pu.data(), pv.data(), K, j, fz, cdw.data(), aw.data() + 8 * s, g_tables.fb_g, tab.data(), tab.data() + 36, 1);
+    for (size_t s = 0; s < n; s++) {
+        uint32_t sg[16];
+        status[s] = stage_msig_finalize(sf.data(), share_ok, offsets[s], offsets[s + 1], s, fz, ru.data(), rv.data(), &bad[s], sg);
+        memcpy(sig + 64 * s, sg, 64);
     }
 }
 int hs_sign(int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, uint8_t* pk_out, uint8_t* sig_out) {

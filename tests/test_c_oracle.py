@@ -114,3 +114,27 @@ def test_generated_batches_are_deterministic_and_shardable():
     b1 = co.gen_single(42, 32, first=32)
     for x, y0, y1 in zip(a, b0, b1):
         assert np.array_equal(x, np.concatenate([y0, y1]))
+
+
+def test_multisig_combine_oracles_and_kat():
+    """multisig::combine: both oracles reproduce the pinned shares -> signature step of reference src/multisig.rs:544-735
+    and agree with each other on generated sessions (incl. a tampered share)."""
+    k = KAT["multisig_kat"]
+    arr = lambda xs: _a(b"".join(bytes.fromhex(x) for x in xs))
+    st, bad, sig, ok = co.multisig_combine(arr(k["PUBLIC_KEYS"]), arr(k["R_POINTS"]), arr(k["S_POINTS"]), arr(k["INDIVIDUAL_SHARES"]), [0, 3], _a(o.le32(31)))
+    assert st[0] == 0 and sig.tobytes().hex() == k["SIGNATURE"] and ok.tolist() == [1, 1, 1]
+    ps, bi, psig, oks = o.multisig_combine([bytes.fromhex(x) for x in k["INDIVIDUAL_SHARES"]], [bytes.fromhex(x) for x in k["PUBLIC_KEYS"]],
+                                           [bytes.fromhex(x) for x in k["R_POINTS"]], [bytes.fromhex(x) for x in k["S_POINTS"]], o.le32(31))
+    assert ps == 0 and psig.hex() == k["SIGNATURE"] and all(oks)
+    pks, Rs, Ss, zs, off, msg = co.gen_multisig(5, [1, 2, 3, 4, 2])
+    zs[off[2] + 1, 0] ^= 1
+    st, bad, sig, ok = co.multisig_combine(pks, Rs, Ss, zs, off, msg)
+    for i in range(5):
+        a, b = off[i], off[i + 1]
+        r = o.multisig_combine([zs[j].tobytes() for j in range(a, b)], [pks[j].tobytes() for j in range(a, b)],
+                               [Rs[j].tobytes() for j in range(a, b)], [Ss[j].tobytes() for j in range(a, b)], msg[i].tobytes())
+        assert r[0] == st[i] and (r[2] or bytes(64)) == sig[i].tobytes() and [int(x) for x in r[3]] == ok[a:b].tolist()
+        if st[i] == 0:  # the combined signature verifies under the aggregate key
+            agg = o.point_to_bytes(o.aggregate_pk([o.point_from_bytes(pks[j].tobytes()) for j in range(a, b)]))
+            assert co.verify_single(_a(agg), sig[i], msg[i])[0][0] == 0
+    assert st.tolist() == [0, 0, 5, 0, 0] and bad[2] == 1

@@ -225,3 +225,21 @@ def test_typed_input_twin(L, vi, kind):
     for i, e in enumerate(expected):
         if e is not None and st_o[i] != 3:
             assert st_b[i] == e, (i, e, st_b[i])
+
+
+def test_multisig_combine_twin(L):
+    """multisig::combine stages on the CPU twin against the oracle: valid sessions, a bad share, a swapped commitment,
+    an undecodable key, an empty session, a non-canonical share and a small-order commitment."""
+    signers = [1, 2, 3, 4, 2, 3, 5, 0, 2, 3]
+    pks, Rs, Ss, zs, off, msg = co.gen_multisig(5, signers)
+    zs[off[2] + 1, 0] ^= 1
+    Rs[off[4]] = Rs[off[4] + 1]
+    pks[off[5]] = np.frombuffer(adv.off_curve_encoding(np.random.default_rng(1)), np.uint8)
+    zs[off[8]] = 0xFF
+    Ss[off[9]] = np.frombuffer(adv.torsion()[4], np.uint8)
+    st, bad, sig, ok = co.multisig_combine(pks, Rs, Ss, zs, off, msg)
+    n, K = len(signers), int(off[-1])
+    hst, hbad, hsig, hok = np.zeros(n, np.uint8), np.zeros(n, np.uint32), np.zeros((n, 64), np.uint8), np.zeros(K, np.uint8)
+    L.hs_multisig_combine(_p(pks), _p(Rs), _p(Ss), _p(zs), _p(off), _p(msg), C.c_size_t(n), _p(hok), _p(hst), _p(hbad), _p(hsig))
+    assert np.array_equal(hst, st) and np.array_equal(hbad, bad) and np.array_equal(hsig, sig) and np.array_equal(hok, ok)
+    assert st.tolist() == [0, 0, 5, 0, 5, 3, 0, 4, 3, 5]
