@@ -7,6 +7,7 @@ the C ABI.  Values are held as the reference's wire encodings; every check runs 
   PublicKeyVarGen, SignatureVarGen            same names                                    (src/keys/public/var_gen.rs, src/signatures/var_gen.rs)
   multisig::aggregate_pk                      multisig_aggregate_pk                         (src/multisig.rs:154-156)
   Error::{InvalidSignature, InvalidPoint, BytesError}   Error enum                          (src/error.rs:13-26)
+  serde (base58 strings of to_bytes())         to_base58 / from_base58                       (src/serde_support.rs)
   (new) verify_batch(&[(PublicKey, Signature, BlsScalar)]) -> Vec<bool>   verify_batch
 
 `verify` returns None for Ok(()) and an Error member for Err(..), so tests read like the reference's:
@@ -74,6 +75,27 @@ def _check_scalar(u: bytes) -> None:
         raise BytesError("InvalidData: scalar is not canonical")
 
 
+_B58 = "123456789ABCDEFGHJKLMNPQRSTUVWXYZabcdefghijkmnopqrstuvwxyz"
+
+
+def b58encode(b: bytes) -> str:
+    n, s = int.from_bytes(b, "big"), ""
+    while n:
+        n, rem = divmod(n, 58)
+        s = _B58[rem] + s
+    return "1" * (len(b) - len(b.lstrip(b"\0"))) + s
+
+
+def b58decode(s: str) -> bytes:
+    n = 0
+    for ch in s:
+        if ch not in _B58:
+            raise BytesError("invalid base58 character")
+        n = n * 58 + _B58.index(ch)
+    pad = len(s) - len(s.lstrip("1"))
+    return b"\0" * pad + (n.to_bytes((n.bit_length() + 7) // 8, "big") if n else b"")
+
+
 class _Wire:
     SIZE = 0
     _points: Tuple[Tuple[int, int], ...] = ()
@@ -99,6 +121,17 @@ class _Wire:
 
     def to_bytes(self) -> bytes:
         return self._raw
+
+    # serde text form of the reference: a base58 (Bitcoin alphabet) string of to_bytes()  (src/serde_support.rs)
+    def to_base58(self) -> str:
+        return b58encode(self._raw)
+
+    @classmethod
+    def from_base58(cls, s: str):
+        b = b58decode(s)
+        if len(b) != cls.SIZE:
+            raise BytesError(f"{cls.__name__}: expected {cls.SIZE} bytes, got {len(b)}")
+        return cls.from_bytes(b)
 
     def __eq__(self, other):
         return type(self) is type(other) and self._raw == other._raw

@@ -76,3 +76,15 @@ def test_workload_classes_have_the_stated_status(variant, gen, ver):
     st, _ = ver(pk, sig, msg)
     assert np.array_equal(st, exp)
     assert set(np.unique(cls).tolist()) == set(range(-1, len(wl.CLASSES)))
+
+
+def test_base58_codec_matches_reference_strings():
+    """The host mirror's base58 (src/serde_support.rs text form) against the pinned strings of tests/serde.rs (CPU only)."""
+    import json
+    from jubjub_schnorr_b200 import api
+    s = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kat.json")))["serde_kat"]
+    for key, size in (("serde_public_key", 32), ("serde_signature", 64), ("serde_public_key_double", 64), ("serde_signature_double", 96),
+                      ("serde_secret_key", 32), ("serde_signature_var_gen", 64)):
+        raw = api.b58decode(s[key])
+        assert len(raw) == size and api.b58encode(raw) == s[key] and raw == o.b58decode(s[key], size)
+    assert api.b58encode(b"\x00\x00\x01") == "112" and api.b58decode("112") == b"\x00\x00\x01"

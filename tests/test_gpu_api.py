@@ -113,3 +113,20 @@ def test_verify_batch(api):
     got = api.verify_batch(items)
     assert got == [i not in (3, 9) for i in range(64)]
     assert api.verify_batch([]) == []
+
+
+def test_serde_base58_round_trip_and_verify(api):  # tests/serde.rs:34-142 (the pinned strings, decoded and verified on the GPU)
+    s = KAT["serde_kat"]
+    pk = api.PublicKey.from_base58(s["serde_public_key"])
+    sig = api.Signature.from_base58(s["serde_signature"])
+    assert pk.to_base58() == s["serde_public_key"] and sig.to_base58() == s["serde_signature"]
+    m = bytes.fromhex("6dfe107145b1cba63d5f5ed0c410c09441fbc0d70c9bfea970949499aa128214")
+    assert pk.verify(sig, m) is None
+    pkd = api.PublicKeyDouble.from_base58(s["serde_public_key_double"])
+    assert pkd.verify(api.SignatureDouble.from_base58(s["serde_signature_double"]), m) is None
+    rng = o.StdRng(s["_seed"]); rng.random_fr(); rng.random_fr()
+    pkv = api.PublicKeyVarGen.from_base58(s["serde_public_key_var_gen"])
+    assert pkv.verify(api.SignatureVarGen.from_base58(s["serde_signature_var_gen"]), rng.random_fq()) is None
+    for bad in (s["serde_too_long_encoded"], s["serde_too_short_encoded"]):  # tests/serde.rs:145-175
+        with pytest.raises(api.BytesError):
+            api.PublicKey.from_base58(bad)
