@@ -24,7 +24,10 @@ using namespace jjs;
 
 namespace {
 
-constexpr int BLOCK = 128;
+#ifndef JJS_BLOCK
+#define JJS_BLOCK 128
+#endif
+constexpr int BLOCK = JJS_BLOCK;
 #ifndef JJS_EQ_MINBLOCKS
 #define JJS_EQ_MINBLOCKS 3
 #endif
