@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(BLOCK) k_sign_aggregate(const uint8_t* sk, con
 
 struct DeviceState {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t copied = nullptr;
     fq* root_tables = nullptr;
     uint8_t* dlog_hash = nullptr;
     niels* fb_g = nullptr;
@@ -481,6 +482,9 @@ int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, c
     const size_t g = ctx->dev.size();
     const size_t per = (n + g - 1) / g;
     const size_t pks = pk_size(variant), sgs = sig_size(variant);
+    // Each device's shard is cut into pipeline slices: slice j + 1 is copied in on the copy stream while slice j is
+    // being verified on the compute stream (the kernels of one slice run far longer than its 128-192 B/item copy).
+    const size_t SLICE = size_t(1) << 18;
     for (size_t k = 0; k < g; k++) {
         size_t lo = k * per, hi = lo + per < n ? lo + per : n;
         if (lo >= hi) break;
@@ -489,12 +493,18 @@ int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, c
         int rc = ensure_staging(ctx, d, m);
         if (rc) return rc;
         JJS_CUDA(ctx, cudaSetDevice(d.device));
-        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_pk, pk + lo * pks, m * pks, cudaMemcpyHostToDevice, d.stream));
-        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_sig, sig + lo * sgs, m * sgs, cudaMemcpyHostToDevice, d.stream));
-        JJS_CUDA(ctx, cudaMemcpyAsync(d.s_msg, msg + lo * 32, m * 32, cudaMemcpyHostToDevice, d.stream));
-        rc = run_device(ctx, d, variant, d.s_pk, d.s_sig, d.s_msg, m, d.s_status, (c_out || challenge_only) ? d.s_c : nullptr, d.stream,
-                        challenge_only);
-        if (rc) return rc;
+        uint8_t* dc = (c_out || challenge_only) ? d.s_c : nullptr;
+        for (size_t off = 0; off < m; off += SLICE) {
+            size_t cnt = m - off < SLICE ? m - off : SLICE;
+            JJS_CUDA(ctx, cudaMemcpyAsync(d.s_pk + off * pks, pk + (lo + off) * pks, cnt * pks, cudaMemcpyHostToDevice, d.copy_stream));
+            JJS_CUDA(ctx, cudaMemcpyAsync(d.s_sig + off * sgs, sig + (lo + off) * sgs, cnt * sgs, cudaMemcpyHostToDevice, d.copy_stream));
+            JJS_CUDA(ctx, cudaMemcpyAsync(d.s_msg + off * 32, msg + (lo + off) * 32, cnt * 32, cudaMemcpyHostToDevice, d.copy_stream));
+            JJS_CUDA(ctx, cudaEventRecord(d.copied, d.copy_stream));
+            JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.copied, 0));
+            rc = run_device(ctx, d, variant, d.s_pk + off * pks, d.s_sig + off * sgs, d.s_msg + off * 32, cnt, d.s_status + off, dc ? dc + off * 32 : nullptr,
+                            d.stream, challenge_only);
+            if (rc) return rc;
+        }
         if (!challenge_only) JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, d.s_status, m, cudaMemcpyDeviceToHost, d.stream));
         if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + lo * 32, d.s_c, m * 32, cudaMemcpyDeviceToHost, d.stream));
     }
@@ -815,6 +825,8 @@ int init_device(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaGetDeviceProperties(&prop, d.device));
     if (prop.major != 10) return fail(ctx, JJS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", d.device, prop.major, prop.minor);
     JJS_CUDA(ctx, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    JJS_CUDA(ctx, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    JJS_CUDA(ctx, cudaEventCreateWithFlags(&d.copied, cudaEventDisableTiming));
     JJS_CUDA(ctx, cudaMalloc(&d.root_tables, sizeof(tables::ROOT_TABLES)));
     JJS_CUDA(ctx, cudaMemcpy(d.root_tables, tables::ROOT_TABLES, sizeof(tables::ROOT_TABLES), cudaMemcpyHostToDevice));
     JJS_CUDA(ctx, cudaMalloc(&d.dlog_hash, sizeof(tables::DLOG_HASH)));
@@ -838,6 +850,8 @@ void free_device(DeviceState& d) {
     cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
     cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.agg_stage); cudaFree(d.d_order);
     if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+    if (d.copied) cudaEventDestroy(d.copied);
 }
 
 int device_entry(jjs_ctx* ctx, int variant, int device_index, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
