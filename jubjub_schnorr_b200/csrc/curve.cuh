@@ -468,6 +468,32 @@ JJS_HD void straus2(ext& r, const fq* tabA, const fq* tabB, size_t stride, const
     r = acc;
 }
 
+// acc = sum_b sum_i 16^i d[b][i] * P_b for NB <= 4 variable bases (64 signed radix-16 digits each) sharing one doubling
+// chain; table b lives at tab + b * 36 * stride.  acc.T is defined on return.
+JJS_HD void straus_multi(ext& r, int nb, const fq* tab, size_t stride, const int8_t (*digits)[64]) {
+    ext acc, t;
+    pniels n;
+    ext_identity(acc);
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+            ext_dbl<false>(t, acc);
+            ext_dbl<false>(acc, t);
+            ext_dbl<false>(t, acc);
+            ext_dbl<true>(acc, t);
+        }
+#pragma unroll 1
+        for (int b = 0; b < nb; b++) {
+            int d = digits[b][i];
+            pniels_load(n, tab + (size_t)b * 36 * stride, stride, d < 0 ? -d : d);
+            pniels_cneg(n, d < 0);
+            ext_add_pniels<true>(t, acc, n);
+            acc = t;
+        }
+    }
+    r = acc;
+}
+
 // r = k * B for a fixed base with precomputed window tables: sum over windows of table[w][k_w] (mixed additions)
 JJS_HD void fixedbase_mul(ext& r, const niels* table, const uint32_t* k) {
     ext acc;

@@ -35,7 +35,7 @@ constexpr int BLOCK = JJS_BLOCK;
 #define JJS_DEC_MINBLOCKS 4
 #endif
 constexpr size_t CHUNK_ITEMS = size_t(1) << 20;   // items per pipeline pass
-constexpr size_t TAB_THREADS = size_t(1) << 20;   // threads served by the per-thread table scratch (two tables of 1152 B each)
+constexpr size_t TAB_THREADS = size_t(1) << 20;   // threads served by the per-thread table scratch (four tables of 1152 B each)
 
 struct Fields {
     WireField f[4];
@@ -92,8 +92,7 @@ __global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq*
     if (t >= n) return;
     size_t item = order[t];
     uint32_t w[8];
-    stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + t,
-                    tab + 36 * stride + t, stride);
+    stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + t, stride);
     if (agg_out) {
         uint4* o = reinterpret_cast<uint4*>(agg_out + item * 32);
         o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(BLOCK) k_msig_session(MsigBuffers b, size_t K,
     if (t >= n) return;
     size_t s = b.order[t];
     stage_msig_session(b.pu, b.pv, b.pf, K, b.offsets[s], b.offsets[s + 1], msg, zf, s, b.d_words, b.cd_words, b.a_words, b.rsa_u, b.rsa_v, b.sflags,
-                       tab + t, tab + 36 * stride + t, stride);
+                       tab + t, stride);
 }
 __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_msig_share(MsigBuffers b, size_t K, WireField zf, fq* tab, size_t stride, Tables T) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,7 +385,7 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaMalloc(&d.iflags, CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.eqflags, 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.cwords, 32 * CHUNK_ITEMS));
-    JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * 2 * 36 * TAB_THREADS));
+    JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * AGG_GROUP * 36 * TAB_THREADS));
     return JJS_SUCCESS;
 }
 

@@ -29,7 +29,7 @@ JJS_HD void fr_add(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // a,
 // decoded points of the whole batch: index j (pk), K + j (R), 2K + j (S)
 JJS_HD void stage_msig_session(const fq* pu, const fq* pv, const uint8_t* pf, size_t K, uint32_t lo, uint32_t hi, const WireField& msg,
                                const WireField& zf, size_t session, uint32_t* d_words, uint32_t* cd_words, uint32_t* a_words, fq* rsa_u, fq* rsa_v,
-                               uint8_t* sflags, fq* tabA, fq* tabB, size_t stride) {
+                               uint8_t* sflags, fq* tabA, size_t stride) {
     uint32_t w[8];
     fq m;
     wire_load(w, msg, session);
@@ -46,28 +46,7 @@ JJS_HD void stage_msig_session(const fq* pu, const fq* pv, const uint8_t* pf, si
     ext acc;
     ext_identity(acc);
 #pragma unroll 1
-    for (uint32_t j = lo; j < hi; j += 2) {
-        int8_t dA[64], dB[64];
-        ext term, sum;
-        uint32_t d[8];
-        aggregate_coeff_words(d, pu, pv, lo, hi, j);
-        for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
-        recode_signed16(dA, d);
-        varbase_table_build(tabA, stride, pu[j], pv[j]);
-        if (j + 1 < hi) {
-            aggregate_coeff_words(d, pu, pv, lo, hi, j + 1);
-            for (int i = 0; i < 8; i++) d_words[8 * (size_t)(j + 1) + i] = d[i];
-            recode_signed16(dB, d);
-            varbase_table_build(tabB, stride, pu[j + 1], pv[j + 1]);
-            straus2<64>(term, tabA, tabB, stride, dA, dB);
-        } else {
-            varbase_mul<true>(term, tabA, stride, dA);
-        }
-        pniels nt;
-        ext_to_pniels(nt, term);
-        ext_add_pniels<true>(sum, acc, nt);
-        acc = sum;
-    }
+    for (uint32_t j = lo; j < hi; j += AGG_GROUP) aggregate_group(acc, pu, pv, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tabA, stride);
     fq zi, au, av;
     fq_inv(zi, acc.Z);
     fq_mul(au, acc.X, zi);

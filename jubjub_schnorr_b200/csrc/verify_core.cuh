@@ -242,8 +242,32 @@ JJS_HD void aggregate_coeff(int8_t* digits, const fq* keys_u, const fq* keys_v, 
     recode_signed16(digits, d);
 }
 
+constexpr int AGG_GROUP = 4;  // signer keys folded per shared doubling chain (per-thread tables: AGG_GROUP x 1152 B)
+
+// acc += sum_{j in [j0, j1)} d_j * pk_j,  j1 - j0 <= AGG_GROUP;  optionally stores the coefficients d_j (8 words each)
+JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j0, uint32_t j1, uint32_t* d_words,
+                            fq* tab, size_t stride) {
+    int8_t digits[AGG_GROUP][64];
+    int nb = 0;
+#pragma unroll 1
+    for (uint32_t j = j0; j < j1; j++, nb++) {
+        uint32_t d[8];
+        aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
+        if (d_words)
+            for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
+        recode_signed16(digits[nb], d);
+        varbase_table_build(tab + (size_t)nb * 36 * stride, stride, keys_u[j], keys_v[j]);
+    }
+    ext term, sum;
+    straus_multi(term, nb, tab, stride, digits);
+    pniels nt;
+    ext_to_pniels(nt, term);
+    ext_add_pniels<true>(sum, acc, nt);
+    acc = sum;
+}
+
 JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
-                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tabA, fq* tabB, size_t stride) {
+                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride) {
     bool decoded = true;
     for (uint32_t j = lo; j < hi; j++) decoded = decoded && (kflags[j] & PF_DECODED);
     if (!decoded || 2 + 2 * (hi - lo) > JJS_MAX_ABSORB) {
@@ -254,25 +278,8 @@ JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* k
     }
     ext acc;
     ext_identity(acc);
-    // signers are folded two at a time so that each pair shares its 252 doublings (Straus)
 #pragma unroll 1
-    for (uint32_t j = lo; j < hi; j += 2) {
-        int8_t dA[64], dB[64];
-        ext term, sum;
-        aggregate_coeff(dA, keys_u, keys_v, lo, hi, j);
-        varbase_table_build(tabA, stride, keys_u[j], keys_v[j]);
-        if (j + 1 < hi) {
-            aggregate_coeff(dB, keys_u, keys_v, lo, hi, j + 1);
-            varbase_table_build(tabB, stride, keys_u[j + 1], keys_v[j + 1]);
-            straus2<64>(term, tabA, tabB, stride, dA, dB);
-        } else {
-            varbase_mul<true>(term, tabA, stride, dA);
-        }
-        pniels nt;
-        ext_to_pniels(nt, term);
-        ext_add_pniels<true>(sum, acc, nt);
-        acc = sum;
-    }
+    for (uint32_t j = lo; j < hi; j += AGG_GROUP) aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, nullptr, tab, stride);
     fq zi, u, v, one;
     fq_inv(zi, acc.Z);
     fq_mul(u, acc.X, zi);

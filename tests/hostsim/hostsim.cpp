@@ -154,14 +154,14 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
                          uint8_t* c_out, uint8_t* agg_out) {
     ensure_ready();
     size_t K = offsets[n];
-    std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(72);
+    std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(36 * AGG_GROUP);
     std::vector<uint8_t> kf(K), pf(2 * n), itf(n);
     std::vector<uint32_t> cw(8 * n);
     WireField fk{pks, 32}, fR{sig + 32, 64}, fmsg{msg, 32}, fu{sig, 64};
     for (size_t k = 0; k < K; k++) stage_decode(fk, k, ku.data(), kv.data(), kf.data(), k, g_tables);
     for (size_t i = 0; i < n; i++) {
         uint32_t w[8];
-        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), tab.data() + 36, 1);
+        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1);
         memcpy(agg_out + 32 * i, w, 32);
         stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables);
         stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
@@ -220,7 +220,7 @@ void hs_multisig_combine(const uint8_t* pks, const uint8_t* Rs, const uint8_t* S
                          uint8_t* share_ok, uint8_t* status, uint32_t* bad, uint8_t* sig) {
     ensure_ready();
     size_t K = offsets[n];
-    std::vector<fq> pu(3 * K + 1), pv(3 * K + 1), tab(72), ru(n), rv(n);
+    std::vector<fq> pu(3 * K + 1), pv(3 * K + 1), tab(36 * AGG_GROUP), ru(n), rv(n);
     std::vector<uint8_t> pf(3 * K + 1), sf(n);
     std::vector<uint32_t> dw(8 * K + 8), cdw(8 * K + 8), aw(8 * n);
     WireField f[3] = {{pks, 32}, {Rs, 32}, {Ss, 32}}, fmsg{msg, 32}, fz{zs, 32};
@@ -228,7 +228,7 @@ void hs_multisig_combine(const uint8_t* pks, const uint8_t* Rs, const uint8_t* S
         for (size_t j = 0; j < K; j++) stage_decode(f[s], j, pu.data(), pv.data(), pf.data(), s * K + j, g_tables, false);
     for (size_t s = 0; s < n; s++)
         stage_msig_session(pu.data(), pv.data(), pf.data(), K, offsets[s], offsets[s + 1], fmsg, fz, s, dw.data(), cdw.data(), aw.data(), ru.data(), rv.data(),
-                           sf.data(), tab.data(), tab.data() + 36, 1);
+                           sf.data(), tab.data(), 1);
     for (size_t s = 0; s < n; s++)
         for (uint32_t j = offsets[s]; j < offsets[s + 1]; j++)
             share_ok[j] = sf[s] == (SF_DECODED | SF_NONEMPTY) &&
