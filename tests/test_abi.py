@@ -88,3 +88,9 @@ def test_base58_codec_matches_reference_strings():
         raw = api.b58decode(s[key])
         assert len(raw) == size and api.b58encode(raw) == s[key] and raw == o.b58decode(s[key], size)
     assert api.b58encode(b"\x00\x00\x01") == "112" and api.b58decode("112") == b"\x00\x00\x01"
+
+
+def test_header_is_plain_c(tmp_path):
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-c", os.path.join(ROOT, "tests", "cpp", "abi_c_check.c"),
+                           "-o", str(tmp_path / "abi_c_check.o")])

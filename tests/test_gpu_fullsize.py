@@ -84,3 +84,51 @@ def test_aggregate_workload_full_size(bv):
                                stream=torch.cuda.current_stream(dev).cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(d_st.cpu().numpy(), expected)
+
+
+def test_chunk_boundaries(bv):
+    """Batches that straddle the internal 2^20-item pass and the 2^18-item copy slices of the host path."""
+    from jubjub_schnorr_b200 import workload as wl
+    for variant, n in ((0, (1 << 20) + 3), (1, (1 << 19) + (1 << 18) + 5)):
+        pk, sig, msg, expected, _ = wl.make_batch(bv, variant, n, 0.05, seed=77 + variant)
+        st = {0: bv.verify_single, 1: bv.verify_double}[variant](pk, sig, msg)
+        assert np.array_equal(st, expected)
+
+
+def test_two_contexts_on_two_host_threads(bv):
+    """Contexts are independent: two host threads, each with its own context on the same GPU, get correct results."""
+    import threading
+    from jubjub_schnorr_b200 import BatchVerifier
+    from jubjub_schnorr_b200 import workload as wl
+    results = {}
+
+    def work(tag, variant):
+        with BatchVerifier([0]) as v:
+            pk, sig, msg, expected, _ = wl.make_batch(v, variant, 60_000, 0.2, seed=900 + tag)
+            for _ in range(3):
+                st = {0: v.verify_single, 2: v.verify_vargen}[variant](pk, sig, msg)
+                results[(tag, _)] = np.array_equal(st, expected)
+
+    threads = [threading.Thread(target=work, args=(i, (0, 2)[i % 2])) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(results) == 6 and all(results.values())
+
+
+def test_argument_errors_are_reported_not_fatal(bv):
+    import ctypes as C
+    from jubjub_schnorr_b200 import _native
+    lib = _native.lib()
+    st = (C.c_uint8 * 4)()
+    buf = (C.c_uint8 * 256)()
+    assert lib.jjs_verify_single(bv._ctx, None, buf, buf, 4, st, None) == -1
+    assert b"null" in lib.jjs_last_error(bv._ctx)
+    assert lib.jjs_verify_single(bv._ctx, buf, buf, buf, 0, st, None) == 0          # empty batch is fine
+    assert lib.jjs_verify_single_device(bv._ctx, 7, buf, buf, buf, 4, st, None, None) == -1
+    assert lib.jjs_challenge_only(bv._ctx, 9, buf, buf, buf, 1, buf) == -1
+    ctx = C.c_void_p()
+    dev = (C.c_int * 1)(99)
+    assert lib.jjs_init(dev, 1, C.byref(ctx)) == -1 and b"not present" in lib.jjs_last_error(ctx)
+    lib.jjs_destroy(ctx)
