@@ -156,11 +156,12 @@ int jjs_sign_aggregate_batch(jjs_ctx* ctx, const uint8_t* sk32, const uint32_t* 
                              const uint8_t* msg32, size_t n, uint8_t* pks32_out, uint8_t* sig64_out);
 
 /* Per-stage device timing (CUDA events on the launching stream around each pipeline stage):
- * stage 0 point decode + subgroup test, 1 challenge hash, 2 key aggregation (aggregate path only), 3 verification
- * equations, 4 status.
+ * stage 0 point decode + subgroup test of the keys, 1 challenge hash, 2 key aggregation (aggregate path only),
+ * 3 verification equations, 4 status, 5 deferred subgroup tests of signature points (only those the equation did not
+ * already settle).
  * jjs_profile_collect waits for the recorded events, adds their durations (ms) and occurrence counts per
  * stage into the two JJS_N_STAGES-long arrays, and clears the records. */
-#define JJS_N_STAGES 5
+#define JJS_N_STAGES 6
 void jjs_profile_enable(jjs_ctx* ctx, int on);
 int jjs_profile_collect(jjs_ctx* ctx, double* stage_ms, uint64_t* stage_count);
 

@@ -67,15 +67,15 @@ class BatchVerifier:
     def launch_count(self) -> int:
         return int(self._lib.jjs_launch_count(self._ctx))
 
-    STAGES = ("decode", "challenge", "aggregate", "equation", "status")
+    STAGES = ("decode", "challenge", "aggregate", "equation", "status", "rtest")
 
     def profile(self, on: bool):
         self._lib.jjs_profile_enable(self._ctx, int(on))
 
     def profile_collect(self):
         """{stage: (total_ms, launches)} since the last collect (waits for the recorded events)."""
-        ms = (C.c_double * 5)()
-        cnt = (C.c_uint64 * 5)()
+        ms = (C.c_double * len(self.STAGES))()
+        cnt = (C.c_uint64 * len(self.STAGES))()
         self._check(self._lib.jjs_profile_collect(self._ctx, ms, cnt), "jjs_profile_collect")
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.STAGES)}
 

@@ -41,14 +41,15 @@ struct Fields {
     WireField f[4];
 };
 
-// thread t < slots * n decodes point field t / n of item t % n into index (slot_base + t / n) * n + t % n
+// thread t < slots * n decodes point field t / n of item t % n into index (slot_base + t / n) * n + t % n;
+// bit s of subgroup_mask: run the subgroup test for slot s now (keys), else leave it to the equation stage (signature points)
 __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode(Fields fields, int slots, int slot_base, size_t n, fq* pts_u, fq* pts_v,
-                                                                      uint8_t* pflags, Tables T, bool want_subgroup) {
+                                                                      uint8_t* pflags, Tables T, uint32_t subgroup_mask) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)slots * n) return;
     int slot = (int)(t / n);
     size_t item = t - (size_t)slot * n;
-    stage_decode(fields.f[slot], item, pts_u, pts_v, pflags, (size_t)(slot_base + slot) * n + item, T, want_subgroup);
+    stage_decode(fields.f[slot], item, pts_u, pts_v, pflags, (size_t)(slot_base + slot) * n + item, T, (subgroup_mask >> slot) & 1u);
 }
 
 // typed inputs: thread t < slots * n normalises point t % slots of item t / slots (item-major, 160 bytes per point)
@@ -114,10 +115,12 @@ __global__ void __launch_bounds__(BLOCK) k_subgroup_check(WireField pts, size_t 
     out[first + t] = subgroup_check(pts, first + t, method, tab + t, stride, T);
 }
 
-// thread t < neq * n : equation t / n of item t % n
-__global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags,
+// thread t < neq * n : equation t / n of item t % n.  Signature points whose subgroup membership the equation did
+// not establish are appended to `rlist` (indices into the point arrays) for k_rtest.
+__global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags,
                                                     const uint8_t* iflags, size_t n, size_t first, size_t count, WireField usc,
-                                                    const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T) {
+                                                    const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T,
+                                                    uint32_t* rlist, uint32_t* rcount) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     size_t g = first + t;
@@ -128,15 +131,24 @@ __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int varian
     for (int s = 0; s < slots; s++) ready = ready && (pflags[s * n + item] & PF_DECODED);
     bool ok = false;
     if (ready) {
-        fq* tabA = tab + t;
-        fq* tabB = tab + 36 * stride + t;
-        if (variant == VAR_SINGLE) ok = stage_equation(pts_u, pts_v, n, item, 0, 1, -1, T.fb_g, usc, cwords, tabA, tabB, stride);
-        else if (variant == VAR_DOUBLE)
-            ok = eq == 0 ? stage_equation(pts_u, pts_v, n, item, 0, 2, -1, T.fb_g, usc, cwords, tabA, tabB, stride)
-                         : stage_equation(pts_u, pts_v, n, item, 1, 3, -1, T.fb_gn, usc, cwords, tabA, tabB, stride);
-        else ok = stage_equation(pts_u, pts_v, n, item, 0, 2, 1, nullptr, usc, cwords, tabA, tabB, stride);
+        bool need_r_test;
+        ok = stage_equation_item(variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
+                                 tab + t, tab + 36 * stride + t, stride, &need_r_test);
+        if (need_r_test) {
+            int pk_slot, r_slot, base_slot;
+            equation_slots(variant, eq, pk_slot, r_slot, base_slot);
+            rlist[atomicAdd(rcount, 1u)] = (uint32_t)((size_t)r_slot * n + item);
+        }
     }
     eqflags[g] = ok ? 1 : 0;
+}
+
+// deferred subgroup tests: thread t < *rcount tests point rlist[t]
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_rtest(const fq* pts_u, const fq* pts_v, uint8_t* pflags, const uint32_t* rlist,
+                                                                     const uint32_t* rcount) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *rcount) return;
+    stage_rtest(pts_u, pts_v, pflags, rlist[t]);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_finalize(int variant, const uint8_t* pflags, const uint8_t* iflags, const uint8_t* eqflags,
@@ -305,6 +317,7 @@ struct DeviceState {
     fq *pts_u = nullptr, *pts_v = nullptr, *tab = nullptr;
     uint8_t *pflags = nullptr, *iflags = nullptr, *eqflags = nullptr;
     uint32_t* cwords = nullptr;
+    uint32_t *rlist = nullptr, *rcount = nullptr;  // signature points awaiting the deferred subgroup test
     // decoded signer keys of the aggregate-key path (grown on demand)
     fq *keys_u = nullptr, *keys_v = nullptr;
     uint8_t* kflags = nullptr;
@@ -385,6 +398,8 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaMalloc(&d.iflags, CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.eqflags, 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.cwords, 32 * CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.rlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
+    JJS_CUDA(ctx, cudaMalloc(&d.rcount, sizeof(uint32_t)));
     JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * AGG_GROUP * 36 * TAB_THREADS));
     return JJS_SUCCESS;
 }
@@ -428,6 +443,29 @@ void variant_fields(int variant, const uint8_t* pk, const uint8_t* sig, const ui
 inline size_t pk_size(int variant) { return variant == VAR_SINGLE ? 32 : 64; }
 inline size_t sig_size(int variant) { return variant == VAR_DOUBLE ? 96 : 64; }
 
+// keys (and the var-gen generator) get their subgroup test in k_decode; signature points get it from the equation
+inline uint32_t key_slot_mask(int variant) { return variant == VAR_SINGLE ? 1u : 3u; }
+
+// Equation stage for a chunk of m items: the equations, then the deferred subgroup tests they asked for.
+int enqueue_equations(jjs_ctx* ctx, DeviceState& d, int variant, size_t m, const WireField& fu, cudaStream_t stream) {
+    const int neq = variant == VAR_DOUBLE ? 2 : 1;
+    Tables T = d.tables();
+    StageTimer t3(ctx, d.device, 3, stream);
+    JJS_CUDA(ctx, cudaMemsetAsync(d.rcount, 0, sizeof(uint32_t), stream));
+    for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
+        size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
+        k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, d.iflags, m, first, cnt, fu, d.cwords, d.eqflags,
+                                                         d.tab, TAB_THREADS, T, d.rlist, d.rcount);
+        ctx->launches++;
+    }
+    t3.stop(stream);
+    StageTimer t5(ctx, d.device, 5, stream);
+    k_rtest<<<blocks_for(neq * m), BLOCK, 0, stream>>>(d.pts_u, d.pts_v, d.pflags, d.rlist, d.rcount);
+    ctx->launches++;
+    t5.stop(stream);
+    return JJS_SUCCESS;
+}
+
 // Enqueue the whole pipeline for n items (device pointers) on `stream`.
 int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
                uint8_t* status, uint8_t* c_out, cudaStream_t stream, bool challenge_only = false) {
@@ -435,7 +473,6 @@ int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, con
     if (rc) return rc;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
     const int slots = variant_slots(variant);
-    const int neq = variant == VAR_DOUBLE ? 2 : 1;
     Tables T = d.tables();
     for (size_t off = 0; off < n; off += CHUNK_ITEMS) {
         size_t m = n - off < CHUNK_ITEMS ? n - off : CHUNK_ITEMS;
@@ -443,7 +480,7 @@ int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, con
         WireField fmsg, fu;
         variant_fields(variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, pts, fmsg, fu);
         StageTimer t0(ctx, d.device, 0, stream);
-        k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, 0, m, d.pts_u, d.pts_v, d.pflags, T, true);
+        k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, 0, m, d.pts_u, d.pts_v, d.pflags, T, key_slot_mask(variant));
         t0.stop(stream);
         StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
@@ -453,14 +490,8 @@ int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, con
             JJS_CUDA(ctx, cudaMemcpyAsync(c_out + off * 32, d.cwords, 32 * m, cudaMemcpyDeviceToDevice, stream));
             continue;
         }
-        StageTimer t3(ctx, d.device, 3, stream);
-        for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
-            size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
-            k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, d.iflags, m, first, cnt, fu, d.cwords,
-                                                             d.eqflags, d.tab, TAB_THREADS, T);
-            ctx->launches++;
-        }
-        t3.stop(stream);
+        rc = enqueue_equations(ctx, d, variant, m, fu, stream);
+        if (rc) return rc;
         StageTimer t4(ctx, d.device, 4, stream);
         k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, status + off,
                                                        c_out ? c_out + off * 32 : nullptr);
@@ -542,8 +573,8 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
         fk.f[1] = fk.f[2] = fk.f[3] = fr.f[1] = fr.f[2] = fr.f[3] = WireField{nullptr, 0};
         WireField fmsg{d_msg + 32 * off, 32}, fu{d_sig + 64 * off, 64};
         StageTimer t0(ctx, d.device, 0, stream);
-        if (K) k_decode<<<blocks_for(K), BLOCK, 0, stream>>>(fk, 1, 0, K, d.keys_u, d.keys_v, d.kflags, T, false);
-        k_decode<<<blocks_for(m), BLOCK, 0, stream>>>(fr, 1, 1, m, d.pts_u, d.pts_v, d.pflags, T, true);
+        if (K) k_decode<<<blocks_for(K), BLOCK, 0, stream>>>(fk, 1, 0, K, d.keys_u, d.keys_v, d.kflags, T, 0u);
+        k_decode<<<blocks_for(m), BLOCK, 0, stream>>>(fr, 1, 1, m, d.pts_u, d.pts_v, d.pflags, T, 0u);
         t0.stop(stream);
         // counting sort of the chunk's items by signer count (host side; counts above 63 share the last bucket)
         {
@@ -569,15 +600,13 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
         StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
         t1.stop(stream);
-        StageTimer t3(ctx, d.device, 3, stream);
-        k_equation<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, d.iflags, m, 0, m, fu, d.cwords, d.eqflags, d.tab,
-                                                       TAB_THREADS, T);
-        t3.stop(stream);
+        int rc2 = enqueue_equations(ctx, d, VAR_SINGLE, m, fu, stream);
+        if (rc2) return rc2;
         StageTimer t4(ctx, d.device, 4, stream);
         k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d_status + off,
                                                        d_c ? d_c + 32 * off : nullptr);
         t4.stop(stream);
-        ctx->launches += 6;
+        ctx->launches += 5;
     }
     JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
@@ -642,7 +671,7 @@ int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, c
     if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
     if (n == 0) return JJS_SUCCESS;
     if (!pts || !u32 || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
-    const int slots = variant_slots(variant), neq = variant == VAR_DOUBLE ? 2 : 1;
+    const int slots = variant_slots(variant);
     const size_t g = ctx->dev.size(), per = (n + g - 1) / g;
     int rc = JJS_SUCCESS;
     for (size_t k = 0; k < g && rc == JJS_SUCCESS; k++) {
@@ -676,14 +705,7 @@ int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, c
             StageTimer t1(ctx, d.device, 1, d.stream);
             k_challenge<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
             t1.stop(d.stream);
-            StageTimer t3(ctx, d.device, 3, d.stream);
-            for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
-                size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
-                k_equation<<<blocks_for(cnt), BLOCK, 0, d.stream>>>(variant, d.pts_u, d.pts_v, d.pflags, d.iflags, m, first, cnt, fu, d.cwords, d.eqflags,
-                                                                   d.tab, TAB_THREADS, T);
-                ctx->launches++;
-            }
-            t3.stop(d.stream);
+            if (enqueue_equations(ctx, d, variant, m, fu, d.stream)) rc = JJS_ERR_CUDA;
             k_finalize<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, b_st, c_out ? b_c : nullptr);
             ctx->launches += 3;
             cudaMemcpyAsync(status + off, b_st, m, cudaMemcpyDeviceToHost, d.stream);
@@ -767,7 +789,7 @@ int run_msig(jjs_ctx* ctx, const uint8_t* pks, const uint8_t* Rs, const uint8_t*
         Fields f;
         f.f[0] = WireField{B + o_pk, 32}; f.f[1] = WireField{B + o_R, 32}; f.f[2] = WireField{B + o_S, 32}; f.f[3] = WireField{nullptr, 0};
         WireField fmsg{B + o_msg, 32}, fz{B + o_z, 32};
-        if (K) k_decode<<<blocks_for(3 * K), BLOCK, 0, st>>>(f, 3, 0, K, b.pu, b.pv, b.pf, T, false);
+        if (K) k_decode<<<blocks_for(3 * K), BLOCK, 0, st>>>(f, 3, 0, K, b.pu, b.pv, b.pf, T, 0u);
         k_msig_session<<<blocks_for(m), BLOCK, 0, st>>>(b, K, m, fmsg, fz, d.tab, TAB_THREADS);
         if (K) k_msig_share<<<blocks_for(K), BLOCK, 0, st>>>(b, K, fz, d.tab, TAB_THREADS, T);
         k_msig_finalize<<<blocks_for(m), BLOCK, 0, st>>>(b, m, fz, B + o_st, reinterpret_cast<uint32_t*>(B + o_bad), B + o_sig);
@@ -845,7 +867,7 @@ void free_device(DeviceState& d) {
     if (d.device < 0) return;
     cudaSetDevice(d.device);
     cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
-    cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords);
+    cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords); cudaFree(d.rlist); cudaFree(d.rcount);
     cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
     cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.agg_stage); cudaFree(d.d_order);
     if (d.stream) cudaStreamDestroy(d.stream);

@@ -54,7 +54,13 @@ JJS_HD double limbs_to_double(const uint32_t* a) {
 // multipliers for the two variable bases.  Quotients are estimated from below in double precision (the margin
 // 2^-40 dwarfs the 2^-49 conversion error) and capped at 2^31 - 1; the exact comparison a >= b drives the loop, so
 // an underestimate only costs another pass.  Huge quotients are consumed 32 bits at a time.
-JJS_HD void half_gcd(uint32_t* tau4, uint32_t* rho4, bool& rho_neg, const uint32_t* c8) {
+//
+// Consecutive cofactors of the Euclidean sequence are coprime, so when the stopping pair has an even rho the pair one
+// step earlier (remainder a >= 2^126, cofactor ta < rho) has an odd one; it is returned instead when its remainder
+// still fits the 33 signed radix-16 digits of the equation kernel (a < 2^130, the usual case: a * rho <= r).  An odd
+// rho is what lets the equation kernel skip the subgroup test of R (verify_core.cuh, stage_equation): rho_odd reports
+// whether one was found.  tau has 5 limbs (< 2^130), rho 4.
+JJS_HD void half_gcd(uint32_t* tau5, uint32_t* rho4, bool& rho_neg, bool& rho_odd, const uint32_t* c8) {
     uint32_t a[8], b[8], ta[4] = {0, 0, 0, 0}, tb[4] = {1, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 8; i++) { a[i] = JJS_C(R_ORDER)[i]; b[i] = c8[i]; }
@@ -108,9 +114,12 @@ JJS_HD void half_gcd(uint32_t* tau4, uint32_t* rho4, bool& rho_neg, const uint32
         for (int i = 0; i < 4; i++) { uint32_t x = ta[i]; ta[i] = tb[i]; tb[i] = x; }
         neg = !neg;
     }
+    bool prev = !(tb[0] & 1u) && (ta[0] & 1u) && (a[7] | a[6] | a[5]) == 0u && a[4] < 4u;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { tau4[i] = b[i]; rho4[i] = tb[i]; }
-    rho_neg = neg;
+    for (int i = 0; i < 4; i++) { tau5[i] = prev ? a[i] : b[i]; rho4[i] = prev ? ta[i] : tb[i]; }
+    tau5[4] = prev ? a[4] : 0u;
+    rho_neg = prev ? !neg : neg;
+    rho_odd = (rho4[0] & 1u) != 0u;
 }
 
 // signed radix-16 digits d_i in [-8, 8) of a little-endian scalar of NLIMBS limbs; writes 8 * NLIMBS + 1 digits
@@ -126,6 +135,13 @@ JJS_HD void recode_signed16_n(int8_t* digits, const uint32_t* k, bool negate) {
         digits[i] = (int8_t)(negate ? -d : d);
     }
     digits[8 * NLIMBS] = (int8_t)(negate ? -(int)carry : (int)carry);
+}
+
+// 33 signed radix-16 digits of a 5-limb scalar below 2^130 (digit 32 takes bits 128..129 and the carry: at most 4)
+JJS_HD void recode_signed16_33(int8_t* digits, const uint32_t* k5, bool negate) {
+    recode_signed16_n<4>(digits, k5, negate);
+    int top = (int)(k5[4] & 3u);
+    digits[32] = (int8_t)(negate ? digits[32] - top : digits[32] + top);
 }
 
 }  // namespace jjs

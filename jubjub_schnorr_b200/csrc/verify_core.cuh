@@ -18,6 +18,7 @@ enum Variant : int { VAR_SINGLE = 0, VAR_DOUBLE = 1, VAR_VARGEN = 2 };
 constexpr uint8_t PF_DECODED = 1;       // from_bytes succeeded
 constexpr uint8_t PF_IDENTITY = 2;      // is_identity()
 constexpr uint8_t PF_TORSION_FREE = 4;  // is_torsion_free()
+constexpr uint8_t PF_TORSION_PENDING = 8;  // subgroup test deferred to the equation stage (signature points, see stage_equation)
 // item flags
 constexpr uint8_t IF_SCALARS_OK = 1;    // u < r and m < q
 constexpr uint8_t IF_EQ0_OK = 2;
@@ -51,7 +52,8 @@ JJS_HD void stage_decode(const WireField& f, size_t item, fq* out_u, fq* out_v, 
         fq one;
         fq_one(one);
         fl = PF_DECODED | ((fq_is_zero(u) && fq_eq(v, one)) ? PF_IDENTITY : 0);
-        if (want_subgroup && point_is_torsion_free_tate(u, v)) fl |= PF_TORSION_FREE;
+        if (!want_subgroup) fl |= PF_TORSION_PENDING;
+        else if (point_is_torsion_free_tate(u, v)) fl |= PF_TORSION_FREE;
         out_u[slot_index] = u;
         out_v[slot_index] = v;
     }
@@ -176,27 +178,34 @@ JJS_HD uint8_t subgroup_check(const WireField& f, size_t i, int method, fq* tab,
 
 // ---- stage 4: one verification equation  u*B + c*PK == R ------------------------------------------
 // Two per-thread tables (tabA, tabB).  Fixed base (base_slot < 0, table `fb`): the challenge is split as
-// tau == rho * c (mod r) with 126-bit tau, rho (half_gcd), and the equivalent check
+// tau == rho * c (mod r) with ~126-bit tau, rho (half_gcd), and the equivalent check
 //     (|rho| u mod r) * B  +  sign(rho) tau * PK  -  |rho| * R  ==  O
-// is evaluated with 33 shared-doubling windows instead of 64.  The equivalence needs PK and R in the prime-order
-// subgroup (rho is invertible mod r): callers only use the result when every point passed is_valid(), which is
-// exactly when the reference evaluates the equation.  Variable base (var-gen): u*Gen + c*PK by a 64-window Straus
-// interleave, compared projectively with R.
+// is evaluated with 33 shared-doubling windows instead of 64.  B and PK must lie in the prime-order subgroup (callers
+// only evaluate the equation for keys that passed is_valid(), which is also when the reference does).  R need not:
+// write R = R0 + T with R0 in the subgroup and T in E[8]; the left side is rho (uB + cPK - R0) - rho T, a subgroup
+// part plus a torsion part, and is O only if both vanish.  So
+//     check holds and rho odd   =>  T == O (R is torsion free) and u*B + c*PK == R,
+//     R torsion free            =>  check holds  <=>  u*B + c*PK == R   (rho is invertible mod r).
+// `r_implied` reports the first case: the caller may then take is_torsion_free(R) as established without testing
+// it; in every other case it must run the subgroup test on R and use the returned bool only if R passes.
+// Variable base (var-gen): u*Gen + c*PK by a 64-window Straus interleave, compared projectively with R; equality
+// with Gen, PK in the subgroup puts R there too.
 JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t item, int pk_slot, int r_slot, int base_slot,
-                           const niels* fb, const WireField& usc, const uint32_t* c_words, fq* tabA, fq* tabB, size_t stride) {
+                           const niels* fb, const WireField& usc, const uint32_t* c_words, fq* tabA, fq* tabB, size_t stride,
+                           bool* r_implied = nullptr) {
     uint32_t u[8], c[8];
     wire_load(u, usc, item);
 #pragma unroll
     for (int i = 0; i < 8; i++) c[i] = c_words[item * 8 + i];
     ext acc;
     if (base_slot < 0) {
-        uint32_t tau[4], rho[8];
-        bool rho_neg;
-        half_gcd(tau, rho, rho_neg, c);
+        uint32_t tau[5], rho[8];
+        bool rho_neg, rho_odd;
+        half_gcd(tau, rho, rho_neg, rho_odd, c);
 #pragma unroll
         for (int i = 4; i < 8; i++) rho[i] = 0;
         int8_t dT[33], dR[33];
-        recode_signed16_n<4>(dT, tau, rho_neg);
+        recode_signed16_33(dT, tau, rho_neg);
         recode_signed16_n<4>(dR, rho, true);
         varbase_table_build(tabA, stride, pts_u[pk_slot * n + item], pts_v[pk_slot * n + item]);
         varbase_table_build(tabB, stride, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
@@ -208,7 +217,9 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
         pniels nb;
         ext_to_pniels(nb, ub);
         ext_add_pniels<false>(sum, acc, nb);
-        return ext_is_identity(sum);
+        bool ok = ext_is_identity(sum);
+        if (r_implied) *r_implied = ok && rho_odd;
+        return ok;
     }
     int8_t dU[64], dC[64];
     recode_signed16(dU, u);
@@ -216,7 +227,43 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
     varbase_table_build(tabA, stride, pts_u[base_slot * n + item], pts_v[base_slot * n + item]);
     varbase_table_build(tabB, stride, pts_u[pk_slot * n + item], pts_v[pk_slot * n + item]);
     straus2<64>(acc, tabA, tabB, stride, dU, dC);
-    return ext_eq_affine(acc, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
+    bool ok = ext_eq_affine(acc, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
+    if (r_implied) *r_implied = ok;
+    return ok;
+}
+
+// Equation `eq` of an item, with the deferred subgroup test of its signature point folded in.  Returns the equation
+// result and updates the flags of R: PF_TORSION_FREE when the equation implies it; otherwise, if the test is still
+// pending, `*need_r_test` is set and the caller must run point_is_torsion_free_tate on R (stage_rtest) before the
+// status is formed.  Keys (and the generator) that are not valid make the item InvalidPoint whatever R is, so the
+// equation is skipped for them.
+JJS_HD void equation_slots(int variant, int eq, int& pk_slot, int& r_slot, int& base_slot) {
+    if (variant == VAR_SINGLE) { pk_slot = 0; r_slot = 1; base_slot = -1; }
+    else if (variant == VAR_DOUBLE) { pk_slot = eq; r_slot = 2 + eq; base_slot = -1; }
+    else { pk_slot = 0; r_slot = 2; base_slot = 1; }
+}
+JJS_HD bool point_flags_valid(uint8_t f) { return (f & PF_TORSION_FREE) && !(f & PF_IDENTITY); }
+JJS_HD bool stage_equation_item(int variant, int eq, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n, size_t item, const niels* fb,
+                                const WireField& usc, const uint32_t* c_words, fq* tabA, fq* tabB, size_t stride, bool* need_r_test) {
+    int pk_slot, r_slot, base_slot;
+    equation_slots(variant, eq, pk_slot, r_slot, base_slot);
+    *need_r_test = false;
+    if (!point_flags_valid(pflags[pk_slot * n + item])) return false;
+    if (base_slot >= 0 && !point_flags_valid(pflags[base_slot * n + item])) return false;
+    bool implied = false;
+    bool ok = stage_equation(pts_u, pts_v, n, item, pk_slot, r_slot, base_slot, fb, usc, c_words, tabA, tabB, stride, &implied);
+    uint8_t rf = pflags[r_slot * n + item];
+    if (rf & PF_TORSION_PENDING) {
+        if (implied) pflags[r_slot * n + item] = (uint8_t)((rf & ~PF_TORSION_PENDING) | PF_TORSION_FREE);
+        else *need_r_test = true;
+    }
+    return ok;
+}
+// the deferred subgroup test of one decoded point (index into the point arrays)
+JJS_HD void stage_rtest(const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t index) {
+    uint8_t f = (uint8_t)(pflags[index] & ~PF_TORSION_PENDING);
+    if (point_is_torsion_free_tate(pts_u[index], pts_v[index])) f |= PF_TORSION_FREE;
+    pflags[index] = f;
 }
 
 // ---- aggregate key: multisig::aggregate_pk (reference src/multisig.rs:154-156, 393-429) ---------------

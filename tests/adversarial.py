@@ -151,3 +151,51 @@ def make_adversarial(kind: str, pk, sig, msg, seed: int, frac: float = 0.5):
         expected[i] = st
         names[i] = name
     return pk, sig, msg, expected, names
+
+
+def torsion_shifted_signatures(kind: str, n: int, seed: int):
+    """Signatures made by a signer who knows the secret key but shifts the commitment by a small-order point:
+    R = r*B + T with T of order 2, 4 or 8, c = H(R, ...), u = r - c*sk.  Then u*B + c*PK == R - T, so the equation
+    fails only by the torsion part; the reference rejects them in Signature::is_valid (InvalidPoint, status 2).
+    These are the inputs a verifier that skips the subgroup test of R would get wrong: any multiple rho of the
+    equation with rho * T == O holds.  Item i uses T of order 2, 4, 8 in turn; for the double variant R and R' are
+    shifted alternately (i // 3 even: R, odd: R').  Returns (pk, sig, msg, expected_status)."""
+    rng = np.random.default_rng(seed)
+    t = torsion()
+    G_ENC, GN_ENC = o.point_to_bytes(o.G), o.point_to_bytes(o.G_NUMS)
+    pkw = 32 if kind == "single" else 64
+    sigw = 96 if kind == "double" else 64
+    pk = np.zeros((n, pkw), np.uint8)
+    sig = np.zeros((n, sigw), np.uint8)
+    msg = np.zeros((n, 32), np.uint8)
+    for i in range(n):
+        sk = 1 + int.from_bytes(rng.bytes(32), "little") % (o.R_ORDER - 1)
+        r = 1 + int.from_bytes(rng.bytes(32), "little") % (o.R_ORDER - 1)
+        m = int.from_bytes(rng.bytes(64), "little") % o.Q
+        T = t[(2, 4, 8)[i % 3]]
+        if kind == "single":
+            pk_e = co.point_mul(G_ENC, sk)
+            R_e = co.point_add(co.point_mul(G_ENC, r), T)
+            c = co.poseidon_hash(list(co.point_decode(R_e)) + list(co.point_decode(pk_e)) + [m])
+            pts = pk_e, R_e
+        elif kind == "double":
+            pk_e = co.point_mul(G_ENC, sk) + co.point_mul(GN_ENC, sk)
+            R0, R1 = co.point_mul(G_ENC, r), co.point_mul(GN_ENC, r)
+            if (i // 3) % 2 == 0:
+                R0 = co.point_add(R0, T)
+            else:
+                R1 = co.point_add(R1, T)
+            R_e = R0 + R1
+            c = co.poseidon_hash([o.DOUBLE_CHALLENGE_DOMAIN] + list(co.point_decode(R0)) + list(co.point_decode(R1))
+                                 + list(co.point_decode(pk_e[:32])) + list(co.point_decode(pk_e[32:])) + [m])
+        else:
+            gen_e = co.point_mul(G_ENC, 1 + int.from_bytes(rng.bytes(32), "little") % (o.R_ORDER - 1))
+            key_e = co.point_mul(gen_e, sk)
+            pk_e = key_e + gen_e
+            R_e = co.point_add(co.point_mul(gen_e, r), T)
+            c = co.poseidon_hash(list(co.point_decode(R_e)) + list(co.point_decode(key_e)) + list(co.point_decode(gen_e)) + [m])
+        u = (r - c * sk) % o.R_ORDER
+        pk[i] = np.frombuffer(pk_e, np.uint8)
+        sig[i] = np.frombuffer(o.le32(u) + R_e, np.uint8)
+        msg[i] = np.frombuffer(o.le32(m), np.uint8)
+    return pk, sig, msg, np.full(n, 2, np.uint8)

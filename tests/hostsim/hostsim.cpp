@@ -75,7 +75,26 @@ static void ensure_ready() {
     g_ready = true;
 }
 
+// equation stage as the kernels run it: k_equation (stage_equation_item) followed by k_rtest for the points it queued
+static int g_rtests = 0, g_equations = 0;
+static bool equation_with_rtest(int variant, int eq, const fq* pu, const fq* pv, uint8_t* pf, size_t n, size_t i, const WireField& fu, const uint32_t* cw,
+                                fq* tab) {
+    bool need;
+    bool ok = stage_equation_item(variant, eq, pu, pv, pf, n, i, (variant == VAR_DOUBLE && eq == 1) ? g_tables.fb_gn : g_tables.fb_g, fu, cw, tab, tab + 36,
+                                  1, &need);
+    g_equations++;
+    if (need) {
+        int pk_slot, r_slot, base_slot;
+        equation_slots(variant, eq, pk_slot, r_slot, base_slot);
+        stage_rtest(pu, pv, pf, (size_t)r_slot * n + i);
+        g_rtests++;
+    }
+    return ok;
+}
+
 extern "C" {
+// counters of the deferred subgroup tests since the last call (equations evaluated, tests run)
+void hs_rtest_counters(int* equations, int* rtests) { *equations = g_equations; *rtests = g_rtests; g_equations = g_rtests = 0; }
 void hs_mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* t16) { mul_wide(t16, a, b); }
 void hs_sqr_wide(const uint32_t* a, uint32_t* t16) { sqr_wide(t16, a); }
 void hs_redc(const uint32_t* t16, uint32_t* r8) { redc(r8, t16); }
@@ -158,28 +177,33 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
     std::vector<uint8_t> kf(K), pf(2 * n), itf(n);
     std::vector<uint32_t> cw(8 * n);
     WireField fk{pks, 32}, fR{sig + 32, 64}, fmsg{msg, 32}, fu{sig, 64};
-    for (size_t k = 0; k < K; k++) stage_decode(fk, k, ku.data(), kv.data(), kf.data(), k, g_tables);
+    for (size_t k = 0; k < K; k++) stage_decode(fk, k, ku.data(), kv.data(), kf.data(), k, g_tables, false);
     for (size_t i = 0; i < n; i++) {
         uint32_t w[8];
         stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1);
         memcpy(agg_out + 32 * i, w, 32);
-        stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables);
+        stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables, false);
         stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
         bool all = (itf[i] & IF_SCALARS_OK) && (pf[i] & PF_DECODED) && (pf[n + i] & PF_DECODED);
-        if (all && stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
+        if (all && equation_with_rtest(VAR_SINGLE, 0, pu.data(), pv.data(), pf.data(), n, i, fu, cw.data(), tab.data())) itf[i] |= IF_EQ0_OK;
         status[i] = stage_status(VAR_SINGLE, pf.data(), itf[i], n, i);
         if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
     }
 }
-// half-size decomposition: outputs tau (16 bytes), |rho| (16 bytes), returns sign of rho (1 = negative)
-int hs_half_gcd(const uint8_t* c32, uint8_t* tau16, uint8_t* rho16) {
-    uint32_t c[8], tau[4], rho[4];
+// half-size decomposition: outputs tau (20 bytes), |rho| (16 bytes), returns sign of rho (bit 0: negative) and bit 1: rho odd;
+// digits33 (optional, 2 x 33 signed bytes): the radix-16 digits the equation kernel uses for sign(rho) tau and -|rho|
+int hs_half_gcd(const uint8_t* c32, uint8_t* tau20, uint8_t* rho16, int8_t* digits33) {
+    uint32_t c[8], tau[5], rho[4];
     memcpy(c, c32, 32);
-    bool neg;
-    half_gcd(tau, rho, neg, c);
-    memcpy(tau16, tau, 16);
+    bool neg, odd;
+    half_gcd(tau, rho, neg, odd, c);
+    memcpy(tau20, tau, 20);
     memcpy(rho16, rho, 16);
-    return neg;
+    if (digits33) {
+        recode_signed16_33(digits33, tau, neg);
+        recode_signed16_n<4>(digits33 + 33, rho, true);
+    }
+    return (neg ? 1 : 0) | (odd ? 2 : 0);
 }
 int hs_subgroup(const uint8_t* p32, int method) {
     ensure_ready();
@@ -202,14 +226,8 @@ void hs_verify_ext(int variant, const uint8_t* pts, const uint8_t* u32, const ui
         bool all = (itf[i] & IF_SCALARS_OK);
         for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);
         if (all) {
-            if (variant == VAR_SINGLE) {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
-            } else if (variant == VAR_DOUBLE) {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
-                if (stage_equation(pu.data(), pv.data(), n, i, 1, 3, -1, g_tables.fb_gn, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ1_OK;
-            } else {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, 1, nullptr, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
-            }
+            for (int eq = 0; eq < (variant == VAR_DOUBLE ? 2 : 1); eq++)
+                if (equation_with_rtest(variant, eq, pu.data(), pv.data(), pf.data(), n, i, fu, cw.data(), tab.data())) itf[i] |= eq ? IF_EQ1_OK : IF_EQ0_OK;
         }
         status[i] = stage_status(variant, pf.data(), itf[i], n, i);
         if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
@@ -263,20 +281,14 @@ void hs_verify(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t
     std::vector<uint8_t> pf(slots * n), itf(n);
     std::vector<uint32_t> cw(8 * n);
     for (int s = 0; s < slots; s++)
-        for (size_t i = 0; i < n; i++) stage_decode(f[s], i, pu.data(), pv.data(), pf.data(), s * n + i, g_tables);
+        for (size_t i = 0; i < n; i++) stage_decode(f[s], i, pu.data(), pv.data(), pf.data(), s * n + i, g_tables, s < (variant == VAR_SINGLE ? 1 : 2));
     for (size_t i = 0; i < n; i++) stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
     for (size_t i = 0; i < n; i++) {
         bool all = (itf[i] & IF_SCALARS_OK);
         for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);
         if (all) {
-            if (variant == VAR_SINGLE) {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 1, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
-            } else if (variant == VAR_DOUBLE) {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, -1, g_tables.fb_g, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
-                if (stage_equation(pu.data(), pv.data(), n, i, 1, 3, -1, g_tables.fb_gn, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ1_OK;
-            } else {
-                if (stage_equation(pu.data(), pv.data(), n, i, 0, 2, 1, nullptr, fu, cw.data(), tab.data(), tab.data() + 36, 1)) itf[i] |= IF_EQ0_OK;
-            }
+            for (int eq = 0; eq < (variant == VAR_DOUBLE ? 2 : 1); eq++)
+                if (equation_with_rtest(variant, eq, pu.data(), pv.data(), pf.data(), n, i, fu, cw.data(), tab.data())) itf[i] |= eq ? IF_EQ1_OK : IF_EQ0_OK;
         }
         status[i] = stage_status(variant, pf.data(), itf[i], n, i);
         if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);

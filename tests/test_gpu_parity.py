@@ -59,6 +59,24 @@ def test_adversarial_batch_matches_oracle(bv, kind, n):
     assert set(st_g.tolist()) == {0, 1, 2, 3}
 
 
+@pytest.mark.parametrize("kind", ["single", "double", "vargen"])
+def test_torsion_shifted_signatures_are_invalid_points(bv, kind):
+    """R = r*B + T (T of order 2, 4, 8) signed by the key holder: the equation holds up to torsion, so only the
+    (deferred) subgroup test of R rejects them -- mixed into valid items so both branches share warps."""
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    cver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    gver = {"single": bv.verify_single, "double": bv.verify_double, "vargen": bv.verify_vargen}[kind]
+    n = 192
+    fpk, fsig, fmsg, exp = adv.torsion_shifted_signatures(kind, n, seed=3)
+    vpk, vsig, vmsg = gen(0xB201, n)
+    pk, sig, msg = np.empty((2 * n, fpk.shape[1]), np.uint8), np.empty((2 * n, fsig.shape[1]), np.uint8), np.empty((2 * n, 32), np.uint8)
+    pk[0::2], pk[1::2], sig[0::2], sig[1::2], msg[0::2], msg[1::2] = fpk, vpk, fsig, vsig, fmsg, vmsg
+    st_o, c_o = cver(pk, sig, msg)
+    st_g, c_g = gver(pk, sig, msg, True)
+    assert np.array_equal(st_o[0::2], exp) and not st_o[1::2].any()
+    assert np.array_equal(st_g, st_o) and np.array_equal(c_g, c_o)
+
+
 def test_challenge_only_matches_oracle(bv):
     pk, sig, msg = co.gen_single(3, 512)
     _, c_o = co.verify_single(pk, sig, msg)

@@ -184,6 +184,59 @@ def test_pipeline_twin_on_adversarial_batches(L, vi, kind):
     assert np.array_equal(hc, c) and np.array_equal(st, exp)
 
 
+def test_half_size_decomposition(L):
+    """tau == rho * c (mod r) with |tau| < 2^130, 0 < |rho| < 2^126, the digits recompose them, and rho is odd for
+    nearly every challenge (what lets the equation stand in for the subgroup test of R)."""
+    rng = np.random.default_rng(5)
+    cs = [0, 1, 2, o.R_ORDER - 1, o.R_ORDER - 2, 1 << 126, (1 << 126) - 1, (1 << 125) + 1, 1 << 249, (1 << 250) - 1, o.R_ORDER // 2, o.R_ORDER // 3]
+    cs += [int.from_bytes(rng.bytes(32), "little") % (1 << 250) for _ in range(3000)]
+    odd = 0
+    for c in cs:
+        tau_b, rho_b, dig = (C.c_uint8 * 20)(), (C.c_uint8 * 16)(), (C.c_int8 * 66)()
+        fl = L.hs_half_gcd((C.c_uint8 * 32).from_buffer_copy(c.to_bytes(32, "little")), tau_b, rho_b, dig)
+        tau, rho = int.from_bytes(bytes(tau_b), "little"), int.from_bytes(bytes(rho_b), "little")
+        assert 0 < rho < (1 << 126) and tau < (1 << 130), hex(c)
+        srho = -rho if fl & 1 else rho
+        assert (srho * c - tau) % o.R_ORDER == 0, hex(c)
+        assert bool(fl & 2) == bool(rho & 1)
+        odd += (fl >> 1) & 1
+        d = list(dig)
+        assert all(-8 <= x <= 8 for x in d)
+        assert sum(x << (4 * i) for i, x in enumerate(d[:33])) == (-tau if fl & 1 else tau)
+        assert sum(x << (4 * i) for i, x in enumerate(d[33:])) == -rho
+    assert odd > 0.93 * len(cs), odd
+
+
+@pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
+def test_torsion_shifted_signatures_are_invalid_points(L, vi, kind):
+    """Forgeries R = r*B + T (T of small order) by the key holder: the equation holds up to torsion, so only the
+    subgroup test of R rejects them.  The twin must run that test whenever the equation did not settle it."""
+    ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    n = 48
+    pk, sig, msg, exp = adv.torsion_shifted_signatures(kind, n, seed=11)
+    st, c = ver(pk, sig, msg)
+    assert np.array_equal(st, exp)
+    hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
+    eqs, rts = C.c_int(), C.c_int()
+    L.hs_rtest_counters(C.byref(eqs), C.byref(rts))
+    L.hs_verify(vi, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
+    L.hs_rtest_counters(C.byref(eqs), C.byref(rts))
+    assert np.array_equal(hst, st) and np.array_equal(hc, c)
+    # every shifted point was tested explicitly (the un-shifted R' of a double item may be settled by its equation)
+    assert rts.value >= n
+
+
+def test_deferred_subgroup_test_is_rare_on_valid_batches(L):
+    n = 96
+    pk, sig, msg = co.gen_single(0xB200, n)
+    hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
+    eqs, rts = C.c_int(), C.c_int()
+    L.hs_rtest_counters(C.byref(eqs), C.byref(rts))
+    L.hs_verify(0, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
+    L.hs_rtest_counters(C.byref(eqs), C.byref(rts))
+    assert not hst.any() and eqs.value == n and rts.value <= n // 8
+
+
 def test_aggregate_twin(L):
     signers = [1, 2, 3, 4, 2, 3, 5, 2]
     pks, off, sig, msg = co.gen_aggregate(11, signers)
