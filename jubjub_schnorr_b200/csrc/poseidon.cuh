@@ -16,6 +16,8 @@
 #pragma once
 #include "consts.cuh"
 #include "fq.cuh"
+#include <cmath>
+#include <cstring>
 
 namespace jjs {
 
@@ -49,6 +51,64 @@ JJS_HD void mds_lane(fq& out, const fq* s, const uint32_t* ark, uint32_t c0, uin
     redc_one(out.l, v);
 }
 
+// The same linear layer on the FP64 pipe, which B200 issues beside the integer multiply pipe
+// (profiles/r01_microbench_fp64.json: DFMA at ~1.35 cycles per warp instruction per scheduler against ~4.2 for
+// IMAD.WIDE, the two overlapping almost completely).  A 17-bit matrix entry times a 32-bit limb is below 2^49, so
+// a column sum  ark_i + sum_k N[o][k] * s[k].l[i]  < 2^50.5 is EXACT in double precision: every limb is lifted to
+// a double (2^52 + x, bit pattern 0x43300000:x, minus 2^52), one DFMA per (output lane, input lane, limb)
+// accumulates on top of 2^52 + ark_i, and the mantissa of the result is the integer column sum.  Columns are
+// then carried into nine 32-bit limbs and finished by the same single Montgomery step as mds_lane.  This takes
+// 200 of the 235 wide multiplies of a linear layer off the integer pipe.
+JJS_HD double f64_biased_u32(uint32_t x) {  // 2^52 + x
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(0x43300000, (int)x);
+#else
+    uint64_t b = 0x4330000000000000ull | x;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+JJS_HD uint64_t f64_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+JJS_HD void mds_all_fp(fq* o, const fq* s, const uint32_t (*ark)[8]) {
+    // integer Cauchy matrix 360360 / (o + k + 5), indexed by o + k
+    const double N[9] = {72072.0, 60060.0, 51480.0, 45045.0, 40040.0, 36036.0, 32760.0, 30030.0, 27720.0};
+    uint32_t v[5][9];
+    uint64_t carry[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        double d[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) d[k] = f64_biased_u32(s[k].l[i]) - 4503599627370496.0;
+#pragma unroll
+        for (int l = 0; l < 5; l++) {
+            double acc = f64_biased_u32(ark[l][i]);
+#pragma unroll
+            for (int k = 0; k < 5; k++) acc = fma(N[l + k], d[k], acc);
+            uint64_t t = (f64_bits(acc) & 0x000fffffffffffffull) + carry[l];
+            v[l][i] = (uint32_t)t;
+            carry[l] = t >> 32;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 5; l++) {
+        v[l][8] = (uint32_t)carry[l];
+        redc_one(o[l].l, v[l]);
+    }
+}
+
+#ifndef JJS_MDS_FP64
+#define JJS_MDS_FP64 1
+#endif
+
 // In/out: ordinary Montgomery form.
 JJS_HD void hades_permute(fq* s) {
 #pragma unroll
@@ -71,12 +131,16 @@ JJS_HD void hades_permute(fq* s) {
             fq_mul(s[4], s[4], fix);
         }
         fq o[5];
+#if JJS_MDS_FP64
+        mds_all_fp(o, s, JJS_C(HADES_FOLDED_ARK)[rnd]);
+#else
         // integer Cauchy matrix 360360 / (i + k + 5)
         mds_lane(o[0], s, JJS_C(HADES_FOLDED_ARK)[rnd][0], 72072u, 60060u, 51480u, 45045u, 40040u);
         mds_lane(o[1], s, JJS_C(HADES_FOLDED_ARK)[rnd][1], 60060u, 51480u, 45045u, 40040u, 36036u);
         mds_lane(o[2], s, JJS_C(HADES_FOLDED_ARK)[rnd][2], 51480u, 45045u, 40040u, 36036u, 32760u);
         mds_lane(o[3], s, JJS_C(HADES_FOLDED_ARK)[rnd][3], 45045u, 40040u, 36036u, 32760u, 30030u);
         mds_lane(o[4], s, JJS_C(HADES_FOLDED_ARK)[rnd][4], 40040u, 36036u, 32760u, 30030u, 27720u);
+#endif
 #pragma unroll
         for (int i = 0; i < 5; i++) s[i] = o[i];
     }
