@@ -235,3 +235,15 @@ def test_multisig_combine_matches_oracle(bv, tmp_path):
     with open(os.path.join(out, "multisig_combine.json"), "w") as f:
         _json.dump({"path": "jjs_multisig_combine (host buffers, 3 participants per session)", "sessions": nb, "participants": int(off[-1]),
                     "seconds": dt, "sessions_per_s": nb / dt, "shares_per_s": int(off[-1]) / dt}, f)
+
+
+def test_fp64_pipe_multiplier_equals_integer_multiplier_on_device():
+    """csrc/fq_fp.cuh (DFMA, 52-bit limbs) against csrc/fq.cuh (IMAD.WIDE) on 14.5 M random products on the GPU;
+    the CPU twin of the same header is checked against big integers in tests/test_hostsim.py."""
+    import subprocess
+    import __graft_entry__ as entry
+    entry.build_tools()
+    out = subprocess.run([os.path.join(entry.ROOT, "tools", "microbench_fqfp")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    res = json.loads(out.stdout)
+    assert res["mismatches"] == 0 and res["checked"] > 10_000_000

@@ -61,6 +61,7 @@ def test_field_ops(L):
         a %= Q
         b %= Q
         L.hs_fq_mul(arr(a), arr(b), r); assert val(r) == a * b * rinv % Q
+        L.hs_fq_mul_fp(arr(a), arr(b), r); assert val(r) == a * b * rinv % Q, (hex(a), hex(b))   # FP64-pipe multiplier
         L.hs_fq_sqr(arr(a), r); assert val(r) == a * a * rinv % Q
         L.hs_fq_add(arr(a), arr(b), r); assert val(r) == (a + b) % Q
         L.hs_fq_sub(arr(a), arr(b), r); assert val(r) == (a - b) % Q
