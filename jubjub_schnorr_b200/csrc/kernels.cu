@@ -309,6 +309,10 @@ struct DeviceState {
     int device = -1;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t copied = nullptr;
+    // two internal compute streams: consecutive sub-chunks of a batch alternate between them (each on its own half of
+    // the scratch), so the last, partially filled wave of one kernel overlaps the first blocks of the next chunk's
+    cudaStream_t sub[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     fq* root_tables = nullptr;
     uint8_t* dlog_hash = nullptr;
     niels* fb_g = nullptr;
@@ -331,6 +335,20 @@ struct DeviceState {
     size_t stage_items = 0;
     Tables tables() const { return Tables{root_tables, dlog_hash, fb_g, fb_gn}; }
 };
+
+// A slice of the pipeline scratch able to hold `cap` items of the widest variant; `tab` serves `cap` threads (the table
+// scratch keeps its global stride TAB_THREADS).
+struct Region {
+    fq *pts_u, *pts_v, *tab;
+    uint8_t *pflags, *iflags, *eqflags;
+    uint32_t *cwords, *rlist, *rcount;
+    size_t cap;
+};
+inline Region region_of(const DeviceState& d, size_t first_item, size_t cap, int counter) {
+    return Region{d.pts_u + 4 * first_item, d.pts_v + 4 * first_item, d.tab + first_item, d.pflags + 4 * first_item, d.iflags + first_item,
+                  d.eqflags + 2 * first_item, d.cwords + 8 * first_item, d.rlist + 2 * first_item, d.rcount + counter, cap};
+}
+inline Region region_whole(const DeviceState& d) { return region_of(d, 0, CHUNK_ITEMS, 0); }
 
 }  // namespace
 
@@ -399,7 +417,7 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaMalloc(&d.eqflags, 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.cwords, 32 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.rlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
-    JJS_CUDA(ctx, cudaMalloc(&d.rcount, sizeof(uint32_t)));
+    JJS_CUDA(ctx, cudaMalloc(&d.rcount, 2 * sizeof(uint32_t)));
     JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * AGG_GROUP * 36 * TAB_THREADS));
     return JJS_SUCCESS;
 }
@@ -446,58 +464,86 @@ inline size_t sig_size(int variant) { return variant == VAR_DOUBLE ? 96 : 64; }
 // keys (and the var-gen generator) get their subgroup test in k_decode; signature points get it from the equation
 inline uint32_t key_slot_mask(int variant) { return variant == VAR_SINGLE ? 1u : 3u; }
 
-// Equation stage for a chunk of m items: the equations, then the deferred subgroup tests they asked for.
-int enqueue_equations(jjs_ctx* ctx, DeviceState& d, int variant, size_t m, const WireField& fu, cudaStream_t stream) {
+// Equation stage for a chunk of m <= R.cap items: the equations, then the deferred subgroup tests they asked for.
+int enqueue_equations(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant, size_t m, const WireField& fu, cudaStream_t stream) {
     const int neq = variant == VAR_DOUBLE ? 2 : 1;
     Tables T = d.tables();
     StageTimer t3(ctx, d.device, 3, stream);
-    JJS_CUDA(ctx, cudaMemsetAsync(d.rcount, 0, sizeof(uint32_t), stream));
-    for (size_t first = 0; first < neq * m; first += TAB_THREADS) {
-        size_t cnt = neq * m - first < TAB_THREADS ? neq * m - first : TAB_THREADS;
-        k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, d.iflags, m, first, cnt, fu, d.cwords, d.eqflags,
-                                                         d.tab, TAB_THREADS, T, d.rlist, d.rcount);
+    JJS_CUDA(ctx, cudaMemsetAsync(R.rcount, 0, sizeof(uint32_t), stream));
+    for (size_t first = 0; first < neq * m; first += R.cap) {
+        size_t cnt = neq * m - first < R.cap ? neq * m - first : R.cap;
+        k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, R.iflags, m, first, cnt, fu, R.cwords, R.eqflags, R.tab,
+                                                         TAB_THREADS, T, R.rlist, R.rcount);
         ctx->launches++;
     }
     t3.stop(stream);
     StageTimer t5(ctx, d.device, 5, stream);
-    k_rtest<<<blocks_for(neq * m), BLOCK, 0, stream>>>(d.pts_u, d.pts_v, d.pflags, d.rlist, d.rcount);
+    k_rtest<<<blocks_for(neq * m), BLOCK, 0, stream>>>(R.pts_u, R.pts_v, R.pflags, R.rlist, R.rcount);
     ctx->launches++;
     t5.stop(stream);
     return JJS_SUCCESS;
 }
 
-// Enqueue the whole pipeline for n items (device pointers) on `stream`.
+// The whole pipeline for one chunk of m <= R.cap items (device pointers) on `stream`.
+int run_chunk(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t m,
+              uint8_t* status, uint8_t* c_out, cudaStream_t stream, bool challenge_only) {
+    const int slots = variant_slots(variant);
+    Tables T = d.tables();
+    Fields pts;
+    WireField fmsg, fu;
+    variant_fields(variant, pk, sig, msg, pts, fmsg, fu);
+    StageTimer t0(ctx, d.device, 0, stream);
+    k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, 0, m, R.pts_u, R.pts_v, R.pflags, T, key_slot_mask(variant));
+    t0.stop(stream);
+    StageTimer t1(ctx, d.device, 1, stream);
+    k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, fmsg, fu, R.cwords, R.iflags);
+    t1.stop(stream);
+    ctx->launches += 2;
+    if (challenge_only) {
+        JJS_CUDA(ctx, cudaMemcpyAsync(c_out, R.cwords, 32 * m, cudaMemcpyDeviceToDevice, stream));
+        return JJS_SUCCESS;
+    }
+    int rc = enqueue_equations(ctx, d, R, variant, m, fu, stream);
+    if (rc) return rc;
+    StageTimer t4(ctx, d.device, 4, stream);
+    k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(variant, R.pflags, R.iflags, R.eqflags, R.cwords, m, status, c_out);
+    t4.stop(stream);
+    ctx->launches++;
+    return JJS_SUCCESS;
+}
+
+constexpr size_t SUB_ITEMS = CHUNK_ITEMS / 2;      // items per scratch half
+constexpr size_t SUB_CHUNK = size_t(1) << 18;      // items per sub-chunk of an overlapped batch
+
+// Enqueue the whole pipeline for n items (device pointers); the work is ordered after what `stream` holds now and
+// `stream` waits for it.  Batches above one sub-chunk are cut into sub-chunks that alternate between the two internal
+// streams and scratch halves: kernels of neighbouring sub-chunks overlap, which hides the partially filled last wave
+// of every launch (per-thread work is uniform, so a launch ends with SMs idling for up to one block duration).
+// With per-stage profiling on, everything stays on `stream` so that the stage timers do not overlap.
 int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
                uint8_t* status, uint8_t* c_out, cudaStream_t stream, bool challenge_only = false) {
     int rc = ensure_scratch(ctx, d);
     if (rc) return rc;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
-    const int slots = variant_slots(variant);
-    Tables T = d.tables();
-    for (size_t off = 0; off < n; off += CHUNK_ITEMS) {
-        size_t m = n - off < CHUNK_ITEMS ? n - off : CHUNK_ITEMS;
-        Fields pts;
-        WireField fmsg, fu;
-        variant_fields(variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, pts, fmsg, fu);
-        StageTimer t0(ctx, d.device, 0, stream);
-        k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, 0, m, d.pts_u, d.pts_v, d.pflags, T, key_slot_mask(variant));
-        t0.stop(stream);
-        StageTimer t1(ctx, d.device, 1, stream);
-        k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
-        t1.stop(stream);
-        ctx->launches += 2;
-        if (challenge_only) {
-            JJS_CUDA(ctx, cudaMemcpyAsync(c_out + off * 32, d.cwords, 32 * m, cudaMemcpyDeviceToDevice, stream));
-            continue;
-        }
-        rc = enqueue_equations(ctx, d, variant, m, fu, stream);
-        if (rc) return rc;
-        StageTimer t4(ctx, d.device, 4, stream);
-        k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, status + off,
-                                                       c_out ? c_out + off * 32 : nullptr);
-        t4.stop(stream);
-        ctx->launches++;
+    const bool overlap = !ctx->profile && n > SUB_CHUNK;
+    if (overlap) {
+        JJS_CUDA(ctx, cudaEventRecord(d.fork, stream));
+        for (int k = 0; k < 2; k++) JJS_CUDA(ctx, cudaStreamWaitEvent(d.sub[k], d.fork, 0));
     }
+    const size_t step = overlap ? SUB_CHUNK : CHUNK_ITEMS;
+    size_t i = 0;
+    for (size_t off = 0; off < n; off += step, i++) {
+        size_t m = n - off < step ? n - off : step;
+        Region R = overlap ? region_of(d, (i & 1) * SUB_ITEMS, SUB_ITEMS, (int)(i & 1)) : region_whole(d);
+        rc = run_chunk(ctx, d, R, variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, m,
+                       status ? status + off : nullptr, c_out ? c_out + off * 32 : nullptr, overlap ? d.sub[i & 1] : stream, challenge_only);
+        if (rc) return rc;
+    }
+    if (overlap)
+        for (int k = 0; k < 2; k++) {
+            JJS_CUDA(ctx, cudaEventRecord(d.join[k], d.sub[k]));
+            JJS_CUDA(ctx, cudaStreamWaitEvent(stream, d.join[k], 0));
+        }
     JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
 }
@@ -513,28 +559,41 @@ int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, c
     const size_t per = (n + g - 1) / g;
     const size_t pks = pk_size(variant), sgs = sig_size(variant);
     // Each device's shard is cut into pipeline slices: slice j + 1 is copied in on the copy stream while slice j is
-    // being verified on the compute stream (the kernels of one slice run far longer than its 128-192 B/item copy).
-    const size_t SLICE = size_t(1) << 18;
+    // being verified (the kernels of one slice run far longer than its 128-192 B/item copy), and consecutive slices
+    // alternate between the two internal compute streams and scratch halves, like the sub-chunks of run_device.
+    // The first slice is short so that compute starts early.
     for (size_t k = 0; k < g; k++) {
         size_t lo = k * per, hi = lo + per < n ? lo + per : n;
         if (lo >= hi) break;
         DeviceState& d = ctx->dev[k];
         size_t m = hi - lo;
         int rc = ensure_staging(ctx, d, m);
+        if (!rc) rc = ensure_scratch(ctx, d);
         if (rc) return rc;
         JJS_CUDA(ctx, cudaSetDevice(d.device));
         uint8_t* dc = (c_out || challenge_only) ? d.s_c : nullptr;
-        for (size_t off = 0; off < m; off += SLICE) {
-            size_t cnt = m - off < SLICE ? m - off : SLICE;
+        const bool serial = ctx->profile;  // stage timers must not overlap
+        size_t j = 0;
+        for (size_t off = 0; off < m; j++) {
+            size_t want = j == 0 ? SUB_CHUNK / 4 : SUB_CHUNK;
+            size_t cnt = m - off < want ? m - off : want;
             JJS_CUDA(ctx, cudaMemcpyAsync(d.s_pk + off * pks, pk + (lo + off) * pks, cnt * pks, cudaMemcpyHostToDevice, d.copy_stream));
             JJS_CUDA(ctx, cudaMemcpyAsync(d.s_sig + off * sgs, sig + (lo + off) * sgs, cnt * sgs, cudaMemcpyHostToDevice, d.copy_stream));
             JJS_CUDA(ctx, cudaMemcpyAsync(d.s_msg + off * 32, msg + (lo + off) * 32, cnt * 32, cudaMemcpyHostToDevice, d.copy_stream));
             JJS_CUDA(ctx, cudaEventRecord(d.copied, d.copy_stream));
-            JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.copied, 0));
-            rc = run_device(ctx, d, variant, d.s_pk + off * pks, d.s_sig + off * sgs, d.s_msg + off * 32, cnt, d.s_status + off, dc ? dc + off * 32 : nullptr,
-                            d.stream, challenge_only);
+            cudaStream_t cs = serial ? d.stream : d.sub[j & 1];
+            JJS_CUDA(ctx, cudaStreamWaitEvent(cs, d.copied, 0));
+            Region R = region_of(d, (j & 1) * SUB_ITEMS, SUB_ITEMS, (int)(j & 1));
+            rc = run_chunk(ctx, d, R, variant, d.s_pk + off * pks, d.s_sig + off * sgs, d.s_msg + off * 32, cnt, d.s_status + off,
+                           dc ? dc + off * 32 : nullptr, cs, challenge_only);
             if (rc) return rc;
+            off += cnt;
         }
+        if (!serial)
+            for (int q = 0; q < 2; q++) {
+                JJS_CUDA(ctx, cudaEventRecord(d.join[q], d.sub[q]));
+                JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.join[q], 0));
+            }
         if (!challenge_only) JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, d.s_status, m, cudaMemcpyDeviceToHost, d.stream));
         if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + lo * 32, d.s_c, m * 32, cudaMemcpyDeviceToHost, d.stream));
     }
@@ -600,7 +659,7 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
         StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
         t1.stop(stream);
-        int rc2 = enqueue_equations(ctx, d, VAR_SINGLE, m, fu, stream);
+        int rc2 = enqueue_equations(ctx, d, region_whole(d), VAR_SINGLE, m, fu, stream);
         if (rc2) return rc2;
         StageTimer t4(ctx, d.device, 4, stream);
         k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d_status + off,
@@ -705,7 +764,7 @@ int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, c
             StageTimer t1(ctx, d.device, 1, d.stream);
             k_challenge<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
             t1.stop(d.stream);
-            if (enqueue_equations(ctx, d, variant, m, fu, d.stream)) rc = JJS_ERR_CUDA;
+            if (enqueue_equations(ctx, d, region_whole(d), variant, m, fu, d.stream)) rc = JJS_ERR_CUDA;
             k_finalize<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, b_st, c_out ? b_c : nullptr);
             ctx->launches += 3;
             cudaMemcpyAsync(status + off, b_st, m, cudaMemcpyDeviceToHost, d.stream);
@@ -848,6 +907,11 @@ int init_device(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     JJS_CUDA(ctx, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     JJS_CUDA(ctx, cudaEventCreateWithFlags(&d.copied, cudaEventDisableTiming));
+    JJS_CUDA(ctx, cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) {
+        JJS_CUDA(ctx, cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking));
+        JJS_CUDA(ctx, cudaEventCreateWithFlags(&d.join[k], cudaEventDisableTiming));
+    }
     JJS_CUDA(ctx, cudaMalloc(&d.root_tables, sizeof(tables::ROOT_TABLES)));
     JJS_CUDA(ctx, cudaMemcpy(d.root_tables, tables::ROOT_TABLES, sizeof(tables::ROOT_TABLES), cudaMemcpyHostToDevice));
     JJS_CUDA(ctx, cudaMalloc(&d.dlog_hash, sizeof(tables::DLOG_HASH)));
@@ -873,6 +937,11 @@ void free_device(DeviceState& d) {
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.copied) cudaEventDestroy(d.copied);
+    if (d.fork) cudaEventDestroy(d.fork);
+    for (int k = 0; k < 2; k++) {
+        if (d.sub[k]) cudaStreamDestroy(d.sub[k]);
+        if (d.join[k]) cudaEventDestroy(d.join[k]);
+    }
 }
 
 int device_entry(jjs_ctx* ctx, int variant, int device_index, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
