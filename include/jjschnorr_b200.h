@@ -81,9 +81,11 @@ int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* off
                          uint8_t* aggpk32_or_null);
 
 /* ---- device-buffer entry points: inputs and outputs already live on device `device_index` of the context
- *      (an index into the list given to jjs_init); the work is enqueued on `cuda_stream` (a cudaStream_t used
- *      as is: NULL is the legacy default stream) and is complete when that stream is.  Calls on one context
- *      share its scratch memory, so keep them on one stream or order them yourself.  No host copies. --- */
+ *      (an index into the list given to jjs_init); the work is ordered after everything `cuda_stream` holds at
+ *      the call (a cudaStream_t used as is: NULL is the legacy default stream) and is complete when that stream
+ *      is: batches above 2^18 items run as sub-chunks on two streams of the context, forked from and joined back
+ *      into `cuda_stream` with events.  Calls on one context share its scratch memory, so keep them on one stream
+ *      or order them yourself.  No host copies. --- */
 int jjs_verify_single_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk32, const uint8_t* d_sig64,
                              const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
                              void* cuda_stream);

@@ -55,6 +55,29 @@ def test_device_pointer_entry_matches_host_entry(bv):
     assert np.array_equal(d_st.cpu().numpy(), st) and np.array_equal(d_c.cpu().numpy(), c) and np.array_equal(st, expected)
 
 
+@pytest.mark.parametrize("variant,n", [(0, 3 * (1 << 18) + 12345), (1, (1 << 19) + 777), (2, (1 << 18) + 1)])
+def test_device_pointer_entry_overlapped_sub_chunks(bv, variant, n):
+    """Device-pointer batches above one sub-chunk (2^18 items) are cut into sub-chunks that alternate between two
+    internal streams and scratch halves; the caller's stream must still see the finished result.  Run twice back to
+    back on the same stream (the second pass reuses both scratch halves while the first may still be draining)."""
+    import torch
+    from jubjub_schnorr_b200 import workload as wl
+    pk, sig, msg, expected, _ = wl.make_batch(bv, variant, n, 0.1, seed=31 + variant)
+    dev = torch.device("cuda", 0)
+    d_pk, d_sig, d_msg = (torch.from_numpy(x).to(dev) for x in (pk, sig, msg))
+    d_st = [torch.full((n,), 0xEE, dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_c = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        for k in range(2):
+            bv.verify_device(variant, d_pk.data_ptr(), d_sig.data_ptr(), d_msg.data_ptr(), n, d_st[k].data_ptr(), d_c.data_ptr(), stream=stream.cuda_stream)
+        first = d_st[0].clone()     # ordered after both passes on the caller's stream
+    stream.synchronize()
+    assert np.array_equal(first.cpu().numpy(), expected) and np.array_equal(d_st[1].cpu().numpy(), expected)
+    st, c = {0: bv.verify_single, 1: bv.verify_double, 2: bv.verify_vargen}[variant](pk, sig, msg, True)
+    assert np.array_equal(st, expected) and np.array_equal(d_c.cpu().numpy(), c)
+
+
 def test_aggregate_workload_full_size(bv):
     """2^17 aggregate-key items signed on the GPU (signer counts 2..4), 5 % invalidated: expectation by construction,
     host and device entry points, and an oracle spot check."""
