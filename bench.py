@@ -402,7 +402,9 @@ def main():
     hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     traffic = None
     try:  # DRAM bytes of the dominant kernel per step, from the committed ncu capture (bytes per unit x units in this step)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")))["kernels"]["k_" + dom]
+        import glob
+        traffic_file = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))[-1]   # newest capture
+        tr = json.load(open(traffic_file))["kernels"]["k_" + dom]
         units = {"decode": sum(p.n * SLOTS.get(p.kind, 1) for p in shards[0]), "challenge": sum(p.n for p in shards[0]),
                  "equation": sum(p.n * NEQ.get(p.kind, 1) for p in shards[0]), "aggregate": sum(p.n for p in shards[0] if p.kind == "aggregate")}[dom]
         traffic = tr["dram_bytes_per_unit"] * units
@@ -410,7 +412,7 @@ def main():
         pass
     roofline = {"bound": "int32_mul", "kernel": {"decode": "k_decode", "challenge": "k_challenge", "aggregate": "k_aggregate", "equation": "k_equation"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "TMAC32/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_unit": "DRAM bytes per step (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01b_ncu_traffic.json); secondary: the bound is the multiply pipe",
+                "traffic_unit": "DRAM bytes per step (ncu dram__bytes_read.sum + dram__bytes_write.sum, the newest profiles/r*_ncu_traffic.json); secondary: the bound is the multiply pipe",
                 "peak_source": peak_src,
                 "ms_per_step": stage_ms[dom], "algorithmic_mac32_per_step": canon[dom],
                 "note": "achieved = canonical MAC32 (SURVEY 8(d) / Appendix C operation counts at 136/108 MAC32 per field mul/sqr) of the kernel's units / its measured time; "
