@@ -67,6 +67,12 @@ int jjs_device_count(const jjs_ctx* ctx);
 /* PublicKey::verify for n (key, signature, message) triples.  reference src/keys/public.rs:114-135 */
 int jjs_verify_single(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n,
                       uint8_t* status, uint8_t* c32_or_null);
+/* NEW in this library (BASELINE.json north_star): verify_batch(&[(PublicKey, Signature, BlsScalar)]) -> Vec<bool>.
+ * Same work as jjs_verify_single; the result comes back as a packed accept bitmap, bit (i % 32) of word i / 32 set iff
+ * PublicKey::verify(pk_i, sig_i, msg_i) is Ok (src/keys/public.rs:114-135).  accept_bitmap has (n + 31) / 32 words;
+ * unused high bits of the last word are 0.  The bits are packed on the GPU with one warp ballot per word. */
+int jjs_verify_batch(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n,
+                     uint32_t* accept_bitmap);
 /* PublicKeyDouble::verify.  reference src/keys/public/double.rs:86-117 */
 int jjs_verify_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n,
                       uint8_t* status, uint8_t* c32_or_null);
@@ -94,6 +100,11 @@ int jjs_verify_double_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk
                              void* cuda_stream);
 int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk64, const uint8_t* d_sig64,
                              const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
+                             void* cuda_stream);
+
+/* Pack n status bytes (any *_device entry point's output) into the accept bitmap described at jjs_verify_batch;
+ * enqueued on `cuda_stream`. */
+int jjs_status_bitmap_device(jjs_ctx* ctx, int device_index, const uint8_t* d_status, size_t n, uint32_t* d_accept_bitmap,
                              void* cuda_stream);
 
 /* Aggregate-key verification on device buffers.  d_offsets / h_offsets: the same n + 1 offsets on the device and on

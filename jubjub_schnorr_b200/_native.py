@@ -16,6 +16,7 @@ EXPORTS = [
     "jjs_verify_single", "jjs_verify_double", "jjs_verify_vargen", "jjs_verify_aggregate",
     "jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device",
     "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect", "jjs_subgroup_check", "jjs_verify_aggregate_device", "jjs_sign_aggregate_batch", "jjs_verify_ext", "jjs_points_to_ext", "jjs_multisig_combine",
+    "jjs_verify_batch", "jjs_status_bitmap_device",
 ]
 
 _lib = None
@@ -49,6 +50,10 @@ def lib():
         f = getattr(L, name)
         f.argtypes = [vp, vp, vp, vp, sz, vp, vp]
         f.restype = C.c_int
+    L.jjs_verify_batch.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.jjs_verify_batch.restype = C.c_int
+    L.jjs_status_bitmap_device.argtypes = [vp, C.c_int, vp, sz, vp, vp]
+    L.jjs_status_bitmap_device.restype = C.c_int
     L.jjs_verify_aggregate.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]
     L.jjs_verify_aggregate.restype = C.c_int
     for name in ("jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device"):

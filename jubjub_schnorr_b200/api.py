@@ -220,7 +220,8 @@ def verify_batch(items: Iterable[Tuple[PublicKey, Signature, object]]) -> List[b
     pk = np.frombuffer(b"".join(k.to_bytes() for k, _, _ in items), dtype=np.uint8)
     sig = np.frombuffer(b"".join(s.to_bytes() for _, s, _ in items), dtype=np.uint8)
     msg = np.frombuffer(b"".join(_msg_bytes(m) for _, _, m in items), dtype=np.uint8)
-    return (default_verifier().verify_single(pk, sig, msg) == 0).tolist()
+    bv = default_verifier()
+    return bv.unpack_bitmap(bv.verify_batch(pk, sig, msg), len(items)).tolist()
 
 
 def multisig_aggregate_pk(pk_vec: Sequence[PublicKey]) -> PublicKey:

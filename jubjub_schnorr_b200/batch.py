@@ -94,6 +94,24 @@ class BatchVerifier:
     def verify_single(self, pk32, sig64, msg32, want_challenge=False):
         return self._verify_host(SINGLE, self._lib.jjs_verify_single, "jjs_verify_single", pk32, sig64, msg32, want_challenge)
 
+    def verify_batch(self, pk32, sig64, msg32):
+        """verify_batch(&[(PublicKey, Signature, BlsScalar)]) -> Vec<bool> as a packed bitmap (uint32 words, bit i % 32 of
+        word i // 32) straight from jjs_verify_batch; `unpack_bitmap` turns it into a bool array."""
+        pk, sig, msg = _u8(pk32, 32, "pk"), _u8(sig64, 64, "sig"), _u8(msg32, 32, "msg")
+        n = msg.shape[0]
+        if pk.shape[0] != n or sig.shape[0] != n:
+            raise ValueError("pk, sig and msg must describe the same number of items")
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(self._lib.jjs_verify_batch(self._ctx, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, n, words.ctypes.data), "jjs_verify_batch")
+        return words
+
+    @staticmethod
+    def unpack_bitmap(words, n):
+        return np.unpackbits(np.ascontiguousarray(words, dtype="<u4").view(np.uint8), bitorder="little")[:n].astype(bool)
+
+    def status_bitmap_device(self, d_status, n, d_bitmap, stream=None, device_index=0):
+        self._check(self._lib.jjs_status_bitmap_device(self._ctx, device_index, d_status, n, d_bitmap, stream), "jjs_status_bitmap_device")
+
     def verify_double(self, pk64, sig96, msg32, want_challenge=False):
         return self._verify_host(DOUBLE, self._lib.jjs_verify_double, "jjs_verify_double", pk64, sig96, msg32, want_challenge)
 

@@ -173,6 +173,14 @@ __global__ void __launch_bounds__(BLOCK) k_finalize(int variant, const uint8_t* 
     }
 }
 
+// accept bitmap: bit (i % 32) of word i / 32 is set iff status[i] == 0; one warp ballot per word
+__global__ void __launch_bounds__(BLOCK) k_bitmap(const uint8_t* status, size_t n, uint32_t* words) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = i < n && status[i] == 0;
+    uint32_t w = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && i < n) words[i >> 5] = w;
+}
+
 __global__ void __launch_bounds__(BLOCK) k_fb_table(niels* out, int which) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= FB_WINDOWS * FB_ENTRIES) return;
@@ -332,6 +340,7 @@ struct DeviceState {
     size_t agg_stage_bytes = 0;
     // staging for the host-buffer entry points
     uint8_t *s_pk = nullptr, *s_sig = nullptr, *s_msg = nullptr, *s_status = nullptr, *s_c = nullptr;
+    uint32_t* s_bitmap = nullptr;
     size_t stage_items = 0;
     Tables tables() const { return Tables{root_tables, dlog_hash, fb_g, fb_gn}; }
 };
@@ -425,14 +434,16 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
 int ensure_staging(jjs_ctx* ctx, DeviceState& d, size_t items) {
     if (items <= d.stage_items) return JJS_SUCCESS;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
-    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
+    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c); cudaFree(d.s_bitmap);
     d.s_pk = d.s_sig = d.s_msg = d.s_status = d.s_c = nullptr;
+    d.s_bitmap = nullptr;
     d.stage_items = 0;
     JJS_CUDA(ctx, cudaMalloc(&d.s_pk, 64 * items));
     JJS_CUDA(ctx, cudaMalloc(&d.s_sig, 96 * items));
     JJS_CUDA(ctx, cudaMalloc(&d.s_msg, 32 * items));
     JJS_CUDA(ctx, cudaMalloc(&d.s_status, items));
     JJS_CUDA(ctx, cudaMalloc(&d.s_c, 32 * items));
+    JJS_CUDA(ctx, cudaMalloc(&d.s_bitmap, 4 * ((items + 31) / 32)));
     d.stage_items = items;
     return JJS_SUCCESS;
 }
@@ -550,13 +561,13 @@ int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, con
 
 // Host-buffer path: contiguous shards over the context's devices, one stream each, joined before return.
 int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status,
-             uint8_t* c_out, bool challenge_only = false) {
+             uint8_t* c_out, bool challenge_only = false, uint32_t* bitmap = nullptr) {
     if (!ctx) return JJS_ERR_ARGUMENT;
     ctx->err[0] = 0;
     if (n == 0) return JJS_SUCCESS;
-    if (!pk || !sig || !msg || (!status && !challenge_only) || (challenge_only && !c_out)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    if (!pk || !sig || !msg || (!status && !challenge_only && !bitmap) || (challenge_only && !c_out)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     const size_t g = ctx->dev.size();
-    const size_t per = (n + g - 1) / g;
+    const size_t per = ((n + g - 1) / g + 31) & ~size_t(31);  // shards start on a bitmap word
     const size_t pks = pk_size(variant), sgs = sig_size(variant);
     // Each device's shard is cut into pipeline slices: slice j + 1 is copied in on the copy stream while slice j is
     // being verified (the kernels of one slice run far longer than its 128-192 B/item copy), and consecutive slices
@@ -594,8 +605,13 @@ int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, c
                 JJS_CUDA(ctx, cudaEventRecord(d.join[q], d.sub[q]));
                 JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.join[q], 0));
             }
-        if (!challenge_only) JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, d.s_status, m, cudaMemcpyDeviceToHost, d.stream));
+        if (!challenge_only && status) JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, d.s_status, m, cudaMemcpyDeviceToHost, d.stream));
         if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + lo * 32, d.s_c, m * 32, cudaMemcpyDeviceToHost, d.stream));
+        if (bitmap) {
+            k_bitmap<<<blocks_for(m), BLOCK, 0, d.stream>>>(d.s_status, m, d.s_bitmap);
+            ctx->launches++;
+            JJS_CUDA(ctx, cudaMemcpyAsync(bitmap + lo / 32, d.s_bitmap, 4 * ((m + 31) / 32), cudaMemcpyDeviceToHost, d.stream));
+        }
     }
     for (size_t k = 0; k < g; k++) {
         JJS_CUDA(ctx, cudaSetDevice(ctx->dev[k].device));
@@ -932,7 +948,7 @@ void free_device(DeviceState& d) {
     cudaSetDevice(d.device);
     cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
     cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords); cudaFree(d.rlist); cudaFree(d.rcount);
-    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c);
+    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c); cudaFree(d.s_bitmap);
     cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.agg_stage); cudaFree(d.d_order);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
@@ -1009,6 +1025,22 @@ JJS_API uint64_t jjs_launch_count(const jjs_ctx* ctx) { return ctx ? ctx->launch
 JJS_API int jjs_verify_single(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint8_t* status,
                               uint8_t* c32_or_null) {
     return run_host(ctx, VAR_SINGLE, pk32, sig64, msg32, n, status, c32_or_null);
+}
+JJS_API int jjs_verify_batch(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint32_t* accept_bitmap) {
+    if (ctx && n && !accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_host(ctx, VAR_SINGLE, pk32, sig64, msg32, n, nullptr, nullptr, false, accept_bitmap);
+}
+JJS_API int jjs_status_bitmap_device(jjs_ctx* ctx, int device_index, const uint8_t* d_status, size_t n, uint32_t* d_accept_bitmap, void* cuda_stream) {
+    if (!ctx) return JJS_ERR_ARGUMENT;
+    ctx->err[0] = 0;
+    if (device_index < 0 || (size_t)device_index >= ctx->dev.size()) return fail(ctx, JJS_ERR_ARGUMENT, "device_index out of range");
+    if (n == 0) return JJS_SUCCESS;
+    if (!d_status || !d_accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    JJS_CUDA(ctx, cudaSetDevice(ctx->dev[device_index].device));
+    k_bitmap<<<blocks_for(n), BLOCK, 0, (cudaStream_t)cuda_stream>>>(d_status, n, d_accept_bitmap);
+    ctx->launches++;
+    JJS_CUDA(ctx, cudaGetLastError());
+    return JJS_SUCCESS;
 }
 JJS_API int jjs_verify_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n, uint8_t* status,
                               uint8_t* c32_or_null) {

@@ -199,3 +199,26 @@ def torsion_shifted_signatures(kind: str, n: int, seed: int):
         sig[i] = np.frombuffer(o.le32(u) + R_e, np.uint8)
         msg[i] = np.frombuffer(o.le32(m), np.uint8)
     return pk, sig, msg, np.full(n, 2, np.uint8)
+
+
+def bitflip_fuzz(pk, sig, msg, seed: int, frac: float = 0.75, max_flips: int = 3):
+    """Differential-fuzz input: `frac` of the items get 1..max_flips random single-bit flips anywhere in their key,
+    signature or message bytes (so any field can become non-canonical, leave the curve, change sign, leave the subgroup
+    or simply stop matching).  No expectation is attached: the GPU is compared with the oracle item by item."""
+    rng = np.random.default_rng(seed)
+    pk, sig, msg = pk.copy(), sig.copy(), msg.copy()
+    n = msg.shape[0]
+    widths = (pk.shape[1], sig.shape[1], 32)
+    total = sum(widths) * 8
+    for i in np.nonzero(rng.random(n) < frac)[0]:
+        for _ in range(int(rng.integers(1, max_flips + 1))):
+            # bias half of the flips towards the top byte of a 32-byte field, where the range and sign rules live
+            if rng.random() < 0.5:
+                field = int(rng.integers(0, sum(widths) // 32))
+                bit = field * 256 + 248 + int(rng.integers(0, 8))
+            else:
+                bit = int(rng.integers(0, total))
+            byte, b = divmod(bit, 8)
+            arr, off = (pk, 0) if byte < widths[0] else ((sig, widths[0]) if byte < widths[0] + widths[1] else (msg, widths[0] + widths[1]))
+            arr[i, byte - off] ^= np.uint8(1 << b)
+    return pk, sig, msg

@@ -96,6 +96,25 @@ def test_c_oracle_matches_python_adversarial(kind, n):
     assert set(st.tolist()) == {0, 1, 2, 3}
 
 
+@pytest.mark.parametrize("kind,n", [("single", 64), ("double", 40), ("vargen", 40)])
+def test_c_oracle_matches_python_on_bitflip_fuzz(kind, n):
+    """The two oracles (big-int Python pinned on the reference's vectors, C used at scale) agree on random bit flips,
+    and so do the torsion-shifted forgeries that only Signature::is_valid rejects."""
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    cver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    pver = {"single": o.verify_single, "double": o.verify_double, "vargen": o.verify_var_gen}[kind]
+    pk, sig, msg = gen(0xF022, n)
+    pk, sig, msg = adv.bitflip_fuzz(pk, sig, msg, seed=17)
+    fpk, fsig, fmsg, fexp = adv.torsion_shifted_signatures(kind, 6, seed=2)
+    pk, sig, msg = np.concatenate([pk, fpk]), np.concatenate([sig, fsig]), np.concatenate([msg, fmsg])
+    st, c = cver(pk, sig, msg)
+    assert (st[n:] == 2).all()
+    for i in range(n + 6):
+        ps, pc = pver(pk[i].tobytes(), sig[i].tobytes(), msg[i].tobytes())
+        assert ps == st[i], (i, ps, st[i])
+        assert (pc or bytes(32)) == c[i].tobytes(), i
+
+
 def test_c_oracle_aggregate_matches_python():
     signers = [1, 2, 3, 4, 2, 3]
     pks, off, sig, msg = co.gen_aggregate(11, signers)

@@ -130,3 +130,25 @@ def test_serde_base58_round_trip_and_verify(api):  # tests/serde.rs:34-142 (the 
     for bad in (s["serde_too_long_encoded"], s["serde_too_short_encoded"]):  # tests/serde.rs:145-175
         with pytest.raises(api.BytesError):
             api.PublicKey.from_base58(bad)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 4097, 300_001])
+def test_verify_batch_bitmap(n):
+    """jjs_verify_batch: the accept bitmap packed on the GPU equals status == 0 of jjs_verify_single, for ragged sizes
+    (last word partly filled, several pipeline slices); jjs_status_bitmap_device packs a device status array the same."""
+    import torch
+    from jubjub_schnorr_b200 import BatchVerifier
+    from jubjub_schnorr_b200 import workload as wl
+    with BatchVerifier([0]) as bv:
+        pk, sig, msg, expected, _ = wl.make_batch(bv, 0, n, 0.3, seed=n)
+        words = bv.verify_batch(pk, sig, msg)
+        assert words.shape == ((n + 31) // 32,)
+        bits = bv.unpack_bitmap(words, n)
+        assert np.array_equal(bits, expected == 0)
+        if n % 32:
+            assert int(words[-1]) >> (n % 32) == 0
+        d_st = torch.from_numpy(expected).cuda()
+        d_w = torch.full(((n + 31) // 32,), -1, dtype=torch.int32, device="cuda")
+        bv.status_bitmap_device(d_st.data_ptr(), n, d_w.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_w.cpu().numpy().view(np.uint32), words)

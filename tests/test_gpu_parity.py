@@ -77,6 +77,23 @@ def test_torsion_shifted_signatures_are_invalid_points(bv, kind):
     assert np.array_equal(st_g, st_o) and np.array_equal(c_g, c_o)
 
 
+@pytest.mark.parametrize("kind,n", [("single", 8192), ("double", 4096), ("vargen", 4096)])
+def test_bitflip_fuzz_matches_oracle(bv, kind, n):
+    """Random single-bit flips in keys, signatures and messages (half of them in the top byte of a field): statuses
+    and challenges equal the oracle's on every item."""
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    cver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    gver = {"single": bv.verify_single, "double": bv.verify_double, "vargen": bv.verify_vargen}[kind]
+    pk, sig, msg = gen(0xF022, n)
+    pk, sig, msg = adv.bitflip_fuzz(pk, sig, msg, seed=99)
+    st_o, c_o = cver(pk, sig, msg)
+    st_g, c_g = gver(pk, sig, msg, True)
+    bad = np.nonzero(st_g != st_o)[0]
+    assert bad.size == 0, [(int(i), int(st_g[i]), int(st_o[i])) for i in bad[:10]]
+    assert np.array_equal(c_g, c_o)
+    assert len(set(st_o.tolist())) >= 3      # the fuzz reaches decode failures, invalid points and bad signatures
+
+
 def test_challenge_only_matches_oracle(bv):
     pk, sig, msg = co.gen_single(3, 512)
     _, c_o = co.verify_single(pk, sig, msg)

@@ -238,6 +238,19 @@ def test_deferred_subgroup_test_is_rare_on_valid_batches(L):
     assert not hst.any() and eqs.value == n and rts.value <= n // 8
 
 
+@pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
+def test_pipeline_twin_on_bitflip_fuzz(L, vi, kind):
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    n = 160
+    pk, sig, msg = gen(0xF022, n)
+    pk, sig, msg = adv.bitflip_fuzz(pk, sig, msg, seed=5)
+    st, c = ver(pk, sig, msg)
+    hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
+    L.hs_verify(vi, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
+    assert np.array_equal(hst, st) and np.array_equal(hc, c)
+
+
 def test_aggregate_twin(L):
     signers = [1, 2, 3, 4, 2, 3, 5, 2]
     pks, off, sig, msg = co.gen_aggregate(11, signers)
