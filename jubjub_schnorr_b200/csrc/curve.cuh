@@ -198,34 +198,45 @@ JJS_HD bool ext_eq_affine(const ext& p, const fq& u, const fq& v) {
 // fixed-exponent powers, inversion, square root of a ratio (q - 1 = 2^32 t)
 // ---------------------------------------------------------------------------------------------
 
-// a^((t-1)/2) with the generated sliding-window schedule (odd powers a, a^3, ..., a^15)
-JJS_HD void fq_pow_tm1d2(fq& r, const fq& a) {
+// a^e for a fixed exponent given as a generated sliding-window schedule (odd powers a, a^3, ..., a^15):
+// entries (squarings, index of the odd power to multiply by, or 0xff for none), most significant window first.
+// WHICH = 0: e = (t - 1) / 2 (square root);  WHICH = 1: e = q - 2 (inversion).  The schedules sit in the constant bank.
+template <int WHICH>
+JJS_HD int pow_sched_entry(int s, int k) { return WHICH == 0 ? JJS_C(SQRT_SCHED)[s][k] : JJS_C(INV_SCHED)[s][k]; }
+template <int WHICH>
+JJS_HD void fq_pow_sched(fq& r, const fq& a) {
+    constexpr int LEN = WHICH == 0 ? JJS_SQRT_SCHED_LEN : JJS_INV_SCHED_LEN;
     fq odd[8], a2;
     odd[0] = a;
     fq_sqr(a2, a);
 #pragma unroll 1
     for (int i = 1; i < 8; i++) fq_mul(odd[i], odd[i - 1], a2);
-    fq acc = odd[JJS_C(SQRT_SCHED)[0][1]];
+    fq acc = odd[pow_sched_entry<WHICH>(0, 1)];
 #pragma unroll 1
-    for (int s = 1; s < JJS_SQRT_SCHED_LEN; s++) {
-        int nsq = JJS_C(SQRT_SCHED)[s][0], idx = JJS_C(SQRT_SCHED)[s][1];
+    for (int s = 1; s < LEN; s++) {
+        int nsq = pow_sched_entry<WHICH>(s, 0), idx = pow_sched_entry<WHICH>(s, 1);
 #pragma unroll 1
         for (int k = 0; k < nsq; k++) fq_sqr(acc, acc);
         if (idx != 0xff) fq_mul(acc, acc, odd[idx]);
     }
     r = acc;
 }
-// a^(q-2) (Fermat inversion; inv(0) = 0).  Only used off the hot path (table construction, aggregate keys).
-JJS_HD void fq_inv(fq& r, const fq& a) {
-    fq acc;
-    fq_one(acc);
-#pragma unroll 1
-    for (int i = 254; i >= 0; i--) {
-        fq_sqr(acc, acc);
-        if ((JJS_C(Q_MINUS_2)[i >> 5] >> (i & 31)) & 1) fq_mul(acc, acc, a);
-    }
-    r = acc;
+// a^((t-1)/2)
+JJS_HD void fq_pow_tm1d2(fq& r, const fq& a) { fq_pow_sched<0>(r, a); }
+// a^(q-2) (Fermat inversion; inv(0) = 0): 254 squarings + 61 products instead of the 164 of square-and-multiply
+// On the device the inversion is a real function: it runs once per point or item, and keeping its dynamically
+// indexed table of odd powers in a frame of its own avoids the local-array miscompile noted in DESIGN.md section 8
+// (seen again when this body was inlined into the key-aggregation kernel).
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ fq fq_inv_fn(fq a) {
+    fq r;
+    fq_pow_sched<1>(r, a);
+    return r;
 }
+JJS_HD void fq_inv(fq& r, const fq& a) { r = fq_inv_fn(a); }
+#else
+JJS_HD void fq_inv(fq& r, const fq& a) { fq_pow_sched<1>(r, a); }
+#endif
 
 JJS_HD uint32_t dlog8(const Tables& T, const fq& x) {  // x in mu_256 = <g^(2^24)>: its discrete log
     uint32_t h = (x.l[0] * JJS_DLOG_HASH_MULT) >> (32 - JJS_DLOG_HASH_BITS);

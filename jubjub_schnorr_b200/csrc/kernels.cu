@@ -53,12 +53,14 @@ __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode(Fields fiel
 }
 
 // typed inputs: thread t < slots * n normalises point t % slots of item t / slots (item-major, 160 bytes per point)
-__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode_ext(const uint8_t* pts, int slots, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags) {
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_decode_ext(const uint8_t* pts, int slots, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags,
+                                                                          uint32_t subgroup_mask) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)slots * n) return;
     int slot = (int)(t / n);
     size_t item = t - (size_t)slot * n;
-    stage_decode_ext(WireField{pts + 160 * (size_t)slot, (uint32_t)(160 * slots)}, item, pts_u, pts_v, pflags, (size_t)slot * n + item);
+    stage_decode_ext(WireField{pts + 160 * (size_t)slot, (uint32_t)(160 * slots)}, item, pts_u, pts_v, pflags, (size_t)slot * n + item,
+                     (subgroup_mask >> slot) & 1u);
 }
 
 // test-data utility: wire point -> JubJubExtended coordinates (u z, v z, z, u z, v) for a caller-chosen Montgomery z
@@ -775,7 +777,7 @@ int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, c
             cudaMemcpyAsync(b_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
             WireField fmsg{b_msg, 32}, fu{b_u, 32};
             StageTimer t0(ctx, d.device, 0, d.stream);
-            k_decode_ext<<<blocks_for(slots * m), BLOCK, 0, d.stream>>>(b_pts, slots, m, d.pts_u, d.pts_v, d.pflags);
+            k_decode_ext<<<blocks_for(slots * m), BLOCK, 0, d.stream>>>(b_pts, slots, m, d.pts_u, d.pts_v, d.pflags, key_slot_mask(variant));
             t0.stop(d.stream);
             StageTimer t1(ctx, d.device, 1, d.stream);
             k_challenge<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);

@@ -67,7 +67,8 @@ JJS_HD void stage_decode(const WireField& f, size_t item, fq* out_u, fq* out_v, 
 //   is_identity   = u == 0 and v == z
 //   is_torsion_free on the affine point (meaningful only when on the curve; the three are AND-ed by is_valid()).
 // A coordinate that is not a reduced field element is reported as undecodable.
-JJS_HD void stage_decode_ext(const WireField& f, size_t item, fq* out_u, fq* out_v, uint8_t* out_flags, size_t slot_index) {
+JJS_HD void stage_decode_ext(const WireField& f, size_t item, fq* out_u, fq* out_v, uint8_t* out_flags, size_t slot_index,
+                             bool want_subgroup = true) {
     fq c[5];
     bool reduced = true;
 #pragma unroll
@@ -98,7 +99,11 @@ JJS_HD void stage_decode_ext(const WireField& f, size_t item, fq* out_u, fq* out
     fq_mul(lhs, c[3], c[4]);
     on_curve = on_curve && fq_eq(t, lhs);
     uint8_t fl = PF_DECODED | ((fq_is_zero(c[0]) && fq_eq(c[1], c[2])) ? PF_IDENTITY : 0);
-    if (on_curve && point_is_torsion_free_tate(au, av)) fl |= PF_TORSION_FREE;
+    // a point off the curve is invalid whatever its subgroup status: its test is neither run nor deferred
+    if (on_curve) {
+        if (!want_subgroup) fl |= PF_TORSION_PENDING;
+        else if (point_is_torsion_free_tate(au, av)) fl |= PF_TORSION_FREE;
+    }
     out_u[slot_index] = au;
     out_v[slot_index] = av;
     out_flags[slot_index] = fl;

@@ -222,7 +222,8 @@ void hs_verify_ext(int variant, const uint8_t* pts, const uint8_t* u32, const ui
     WireField fmsg{msg, 32}, fu{u32, 32};
     for (int s = 0; s < slots; s++)
         for (size_t i = 0; i < n; i++)
-            stage_decode_ext(WireField{pts + 160 * s, (uint32_t)(160 * slots)}, i, pu.data(), pv.data(), pf.data(), s * n + i);
+            stage_decode_ext(WireField{pts + 160 * s, (uint32_t)(160 * slots)}, i, pu.data(), pv.data(), pf.data(), s * n + i,
+                             s < (variant == VAR_SINGLE ? 1 : 2));
     for (size_t i = 0; i < n; i++) {
         stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
         bool all = (itf[i] & IF_SCALARS_OK);

@@ -34,16 +34,9 @@ def mont(x):
 # ------------------------------------------------------------------------------------------------
 # square root machinery
 # ------------------------------------------------------------------------------------------------
-def sqrt_constants():
-    t = (Q - 1) >> 32
-    z = 2
-    while pow(z, (Q - 1) // 2, Q) == 1:
-        z += 1
-    g = pow(z, t, Q)  # generator of the 2^32 torsion
-    assert pow(g, 1 << 31, Q) == Q - 1
-    e = (t - 1) // 2
-    # sliding-window (width 4, odd powers 1..15) schedule for the fixed exponent e, MSB first:
-    # list of (squarings, odd power index) ; a trailing (squarings, 0xff) finishes with no multiply
+def window_schedule(e):
+    """Sliding-window (width 4, odd powers 1..15) schedule for the fixed exponent e, MSB first: list of
+    (squarings, odd power index); a trailing (squarings, 0xff) finishes with no multiply.  Self-checked."""
     bits = bin(e)[2:]
     sched, i, pending_sq, first = [], 0, 0, True
     while i < len(bits):
@@ -61,7 +54,6 @@ def sqrt_constants():
         i = j
     if pending_sq:
         sched.append((pending_sq, 0xFF))
-    # self-check
     x = 3
     odd = [pow(x, 2 * k + 1, Q) for k in range(8)]
     acc = None
@@ -74,6 +66,18 @@ def sqrt_constants():
         if idx != 0xFF:
             acc = acc * odd[idx] % Q
     assert acc == pow(x, e, Q)
+    return sched
+
+
+def sqrt_constants():
+    t = (Q - 1) >> 32
+    z = 2
+    while pow(z, (Q - 1) // 2, Q) == 1:
+        z += 1
+    g = pow(z, t, Q)  # generator of the 2^32 torsion
+    assert pow(g, 1 << 31, Q) == Q - 1
+    e = (t - 1) // 2
+    sched = window_schedule(e)
     tabs = {}
     for name, shift in (("T0", 0), ("T1", 8), ("T2", 16), ("H1", 7), ("H2", 15), ("H3", 23)):
         base = pow(g, -(1 << shift), Q)
@@ -373,6 +377,10 @@ def main():
         u(" %s," % limbs(mont(safe_tag(n))))
     u("};")
     u("JJS_CONST_QUAL uint32_t DOUBLE_DOMAIN[8] = %s; /* BlsScalar::from(0x4a4a53434844424c), Montgomery */" % limbs(mont(0x4A4A53434844424C)))
+    # appended last: the constant bank is laid out in declaration order, and the arrays above keep their offsets
+    inv_sched = window_schedule(Q - 2)
+    u("#define JJS_INV_SCHED_LEN %d" % len(inv_sched))
+    u("JJS_CONST_QUAL uint8_t INV_SCHED[JJS_INV_SCHED_LEN][2] = {%s}; /* same encoding as SQRT_SCHED, for a^(q-2) */" % ", ".join("{%d, %d}" % s_ for s_ in inv_sched))
     t("/* Large, data-dependently indexed tables: host arrays, uploaded to device global memory at context creation. */")
     t("static const uint8_t DLOG_HASH[1 << %d] = {%s};" % (sq["hash_bits"], ", ".join(map(str, sq["hash_table"]))))
     t("/* root-of-unity tables, Montgomery: T0,T1,T2 = g^(-j 2^(8i)); H1,H2,H3 = g^(-j 2^(8i-1)); order T0,T1,T2,H1,H2,H3 */")
