@@ -86,16 +86,27 @@ __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_points_to_ext(cons
     }
 }
 
+// one thread hashes the delinearisation coefficients of one item's signer keys (same item order as k_aggregate)
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_agg_coeffs(const fq* keys_u, const fq* keys_v, const uint8_t* kflags,
+                                                                          const uint32_t* offsets, const uint32_t* order, uint32_t key_base, size_t n,
+                                                                          uint32_t* d_words) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    size_t item = order[t];
+    stage_aggregate_coeffs(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, d_words);
+}
+
 // one thread folds the signer keys of one item into its aggregate key (slot 0 of the single-variant point arrays)
 // `order` lists the items sorted by signer count, so the lanes of a warp loop over the same number of signers
 __global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, const uint32_t* offsets,
                                                      const uint32_t* order, uint32_t key_base, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags,
-                                                     uint8_t* agg_out, fq* tab, size_t stride) {
+                                                     uint8_t* agg_out, fq* tab, size_t stride, uint32_t* d_words) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     size_t item = order[t];
     uint32_t w[8];
-    stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + t, stride);
+    stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + t, stride,
+                    d_words);
     if (agg_out) {
         uint4* o = reinterpret_cast<uint4*>(agg_out + item * 32);
         o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -335,6 +346,7 @@ struct DeviceState {
     // decoded signer keys of the aggregate-key path (grown on demand)
     fq *keys_u = nullptr, *keys_v = nullptr;
     uint8_t* kflags = nullptr;
+    uint32_t* kcoef = nullptr;     // delinearisation coefficients, 8 words per key
     size_t cap_keys = 0;
     uint32_t* d_order = nullptr;   // items of a chunk sorted by signer count
     std::vector<uint32_t> h_order;
@@ -637,11 +649,12 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
         size_t K = key_hi - key_lo;
         if (K > d.cap_keys) {
             JJS_CUDA(ctx, cudaStreamSynchronize(stream));
-            cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags);
-            d.keys_u = d.keys_v = nullptr; d.kflags = nullptr; d.cap_keys = 0;
+            cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.kcoef);
+            d.keys_u = d.keys_v = nullptr; d.kflags = nullptr; d.kcoef = nullptr; d.cap_keys = 0;
             JJS_CUDA(ctx, cudaMalloc(&d.keys_u, sizeof(fq) * K));
             JJS_CUDA(ctx, cudaMalloc(&d.keys_v, sizeof(fq) * K));
             JJS_CUDA(ctx, cudaMalloc(&d.kflags, K));
+            JJS_CUDA(ctx, cudaMalloc(&d.kcoef, 32 * K));
             d.cap_keys = K;
         }
         Fields fk, fr;
@@ -671,8 +684,9 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
             JJS_CUDA(ctx, cudaMemcpyAsync(d.d_order, d.h_order.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, stream));
         }
         StageTimer t2(ctx, d.device, 2, stream);
+        k_agg_coeffs<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, d.d_order, key_lo, m, d.kcoef);
         k_aggregate<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, d.d_order, key_lo, m, d.pts_u, d.pts_v,
-                                                        d.pflags, d_agg ? d_agg + 32 * off : nullptr, d.tab, TAB_THREADS);
+                                                        d.pflags, d_agg ? d_agg + 32 * off : nullptr, d.tab, TAB_THREADS, d.kcoef);
         t2.stop(stream);
         StageTimer t1(ctx, d.device, 1, stream);
         k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
@@ -683,7 +697,7 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
         k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d_status + off,
                                                        d_c ? d_c + 32 * off : nullptr);
         t4.stop(stream);
-        ctx->launches += 5;
+        ctx->launches += 6;
     }
     JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
@@ -951,7 +965,7 @@ void free_device(DeviceState& d) {
     cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
     cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords); cudaFree(d.rlist); cudaFree(d.rcount);
     cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c); cudaFree(d.s_bitmap);
-    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.agg_stage); cudaFree(d.d_order);
+    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.kcoef); cudaFree(d.agg_stage); cudaFree(d.d_order);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.copied) cudaEventDestroy(d.copied);

@@ -297,16 +297,21 @@ JJS_HD void aggregate_coeff(int8_t* digits, const fq* keys_u, const fq* keys_v, 
 constexpr int AGG_GROUP = 4;  // signer keys folded per shared doubling chain (per-thread tables: AGG_GROUP x 1152 B)
 
 // acc += sum_{j in [j0, j1)} d_j * pk_j,  j1 - j0 <= AGG_GROUP;  optionally stores the coefficients d_j (8 words each)
+// `d_ready`: the coefficients were computed by an earlier kernel (stage_aggregate_coeffs) and are read from d_words
 JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j0, uint32_t j1, uint32_t* d_words,
-                            fq* tab, size_t stride) {
+                            fq* tab, size_t stride, bool d_ready = false) {
     int8_t digits[AGG_GROUP][64];
     int nb = 0;
 #pragma unroll 1
     for (uint32_t j = j0; j < j1; j++, nb++) {
         uint32_t d[8];
-        aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
-        if (d_words)
-            for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
+        if (d_ready) {
+            for (int i = 0; i < 8; i++) d[i] = d_words[8 * (size_t)j + i];
+        } else {
+            aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
+            if (d_words)
+                for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
+        }
         recode_signed16(digits[nb], d);
         varbase_table_build(tab + (size_t)nb * 36 * stride, stride, keys_u[j], keys_v[j]);
     }
@@ -318,11 +323,30 @@ JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32
     acc = sum;
 }
 
-JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
-                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride) {
+// whether the signer keys [lo, hi) of an item can be aggregated at all (every key decoded, transcript within the sponge tags)
+JJS_HD bool aggregate_ready(const uint8_t* kflags, uint32_t lo, uint32_t hi) {
     bool decoded = true;
     for (uint32_t j = lo; j < hi; j++) decoded = decoded && (kflags[j] & PF_DECODED);
-    if (!decoded || 2 + 2 * (hi - lo) > JJS_MAX_ABSORB) {
+    return decoded && 2 + 2 * (hi - lo) <= JJS_MAX_ABSORB;
+}
+// First half of the aggregation as a stage of its own: the delinearisation coefficients d_j of one item (n hashes of
+// 2 + 2n elements), written as 8 words each to d_words[8 j ..].  Keeping the hashing apart from the multi-scalar
+// multiplication gives two kernels with the register footprint and code size of k_challenge and k_equation.
+JJS_HD void stage_aggregate_coeffs(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, uint32_t* d_words) {
+    if (!aggregate_ready(kflags, lo, hi)) return;
+#pragma unroll 1
+    for (uint32_t j = lo; j < hi; j++) {
+        uint32_t d[8];
+        aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
+#pragma unroll
+        for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
+    }
+}
+
+// d_words: nullptr (coefficients are hashed here) or the output of stage_aggregate_coeffs for the same keys
+JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
+                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride, uint32_t* d_words = nullptr) {
+    if (!aggregate_ready(kflags, lo, hi)) {
         out_flags[out_index] = 0;
         if (agg_wire)
             for (int i = 0; i < 8; i++) agg_wire[i] = 0;
@@ -331,7 +355,8 @@ JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* k
     ext acc;
     ext_identity(acc);
 #pragma unroll 1
-    for (uint32_t j = lo; j < hi; j += AGG_GROUP) aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, nullptr, tab, stride);
+    for (uint32_t j = lo; j < hi; j += AGG_GROUP)
+        aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tab, stride, d_words != nullptr);
     fq zi, u, v, one;
     fq_inv(zi, acc.Z);
     fq_mul(u, acc.X, zi);

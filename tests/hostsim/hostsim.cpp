@@ -177,12 +177,13 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
     size_t K = offsets[n];
     std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(36 * AGG_GROUP);
     std::vector<uint8_t> kf(K), pf(2 * n), itf(n);
-    std::vector<uint32_t> cw(8 * n);
+    std::vector<uint32_t> cw(8 * n), kc(8 * K + 8);
     WireField fk{pks, 32}, fR{sig + 32, 64}, fmsg{msg, 32}, fu{sig, 64};
     for (size_t k = 0; k < K; k++) stage_decode(fk, k, ku.data(), kv.data(), kf.data(), k, g_tables, false);
     for (size_t i = 0; i < n; i++) {
         uint32_t w[8];
-        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1);
+        stage_aggregate_coeffs(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], kc.data());
+        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1, kc.data());
         memcpy(agg_out + 32 * i, w, 32);
         stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables, false);
         stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
