@@ -52,7 +52,7 @@ def main():
     for f in files:
         for k, v in read(f).items():
             kernels.setdefault(k, v)
-    order = [k for k in ("k_decode", "k_challenge", "k_equation", "k_rtest", "k_aggregate") if k in kernels]
+    order = [k for k in ("k_decode", "k_challenge", "k_equation", "k_rtest", "k_agg_coeffs", "k_aggregate") if k in kernels]
     lines = [f"# {tag} ncu summary", "",
              "ncu --set full --clock-control none --import-source on (tools/profile_round.sh); one launch per kernel after warm-up. "
              "Reports stay in gpurun_out/; the launch list of the default bench command is `" + tag + "_launches.csv`.", "",

@@ -20,7 +20,7 @@ python bench.py --log2n 18 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_
 ncu --set full --clock-control none --import-source on -k regex:'k_decode|k_challenge|k_equation|k_rtest' --launch-skip 5 --launch-count 5 \
     -o $out/${tag}_prof_single -f python bench.py --log2n 18 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_single.log 2>&1
 python bench.py --workload aggregate --log2n 17 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_plain_agg.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'k_aggregate' --launch-skip 1 --launch-count 1 \
+ncu --set full --clock-control none --import-source on -k regex:'k_aggregate|k_agg_coeffs' --launch-skip 2 --launch-count 2 \
     -o $out/${tag}_prof_agg -f python bench.py --workload aggregate --log2n 17 --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_agg.log 2>&1
 for r in single agg; do
   [ -f $out/${tag}_prof_$r.ncu-rep ] && ncu -i $out/${tag}_prof_$r.ncu-rep --page raw --csv > $out/${tag}_prof_$r.raw.csv 2>/dev/null
