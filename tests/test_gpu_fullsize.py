@@ -87,10 +87,7 @@ def test_aggregate_workload_full_size(bv):
     pks, off, sig, msg, expected, cls = wl.make_aggregate_batch(bv, n, 0.05, seed=0xA66)
     st, c, agg = bv.verify_aggregate(pks, off, sig, msg, True, True)
     assert np.array_equal(st, expected)
-    idx = np.random.default_rng(3).choice(n - 1, size=300, replace=False)
-    for i in idx[:300]:
-        pass
-    sel = np.sort(idx)
+    sel = np.sort(np.random.default_rng(3).choice(n - 1, size=300, replace=False))
     sub_off = np.zeros(len(sel) + 1, dtype=np.uint32)
     sub_keys = []
     for j, i in enumerate(sel):
