@@ -94,6 +94,18 @@ def test_bitflip_fuzz_matches_oracle(bv, kind, n):
     assert len(set(st_o.tolist())) >= 3      # the fuzz reaches decode failures, invalid points and bad signatures
 
 
+def test_config0_2p16_valid_singles_item_by_item(bv):
+    """BASELINE.json configs[0]: 2^16 random valid single signatures (the reference's CPU-runnable case), every status
+    and every challenge scalar against the oracle, through the host entry point and through verify_batch's bitmap."""
+    n = 1 << 16
+    pk, sig, msg = co.gen_single(0xB200, n)
+    st_o, c_o = co.verify_single(pk, sig, msg)
+    assert not st_o.any()
+    st_g, c_g = bv.verify_single(pk, sig, msg, True)
+    assert np.array_equal(st_g, st_o) and np.array_equal(c_g, c_o)
+    assert bv.unpack_bitmap(bv.verify_batch(pk, sig, msg), n).all()
+
+
 def test_challenge_only_matches_oracle(bv):
     pk, sig, msg = co.gen_single(3, 512)
     _, c_o = co.verify_single(pk, sig, msg)
