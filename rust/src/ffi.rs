@@ -1,0 +1,48 @@
+// Extracted from INTEGRATION.md by tools/extract_rust_shim.py -- edit the markdown, not this file.
+// NOT compiled in this repository's environment (no cargo/rustc in the image).
+
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+#[repr(C)] pub struct jjs_ctx { _private: [u8; 0] }
+
+pub const JJS_OK: u8 = 0;                // Ok(())
+pub const JJS_INVALID_SIGNATURE: u8 = 1; // Error::InvalidSignature   src/error.rs:17
+pub const JJS_INVALID_POINT: u8 = 2;     // Error::InvalidPoint       src/error.rs:19
+pub const JJS_BYTES_ERROR: u8 = 3;       // Error::BytesError(_)      src/error.rs:15
+
+extern "C" {
+    pub fn jjs_init(devices: *const c_int, n_devices: c_int, out: *mut *mut jjs_ctx) -> c_int;
+    pub fn jjs_destroy(ctx: *mut jjs_ctx);
+    pub fn jjs_last_error(ctx: *const jjs_ctx) -> *const c_char;
+    pub fn jjs_device_count(ctx: *const jjs_ctx) -> c_int;
+    // PublicKey::verify                      src/keys/public.rs:114-135
+    pub fn jjs_verify_single(ctx: *mut jjs_ctx, pk32: *const u8, sig64: *const u8, msg32: *const u8, n: usize,
+                             status: *mut u8, c32_or_null: *mut u8) -> c_int;
+    // NEW verify_batch -> packed accept bitmap ((n + 31) / 32 words, bit i % 32 of word i / 32)
+    pub fn jjs_verify_batch(ctx: *mut jjs_ctx, pk32: *const u8, sig64: *const u8, msg32: *const u8, n: usize,
+                            accept_bitmap: *mut u32) -> c_int;
+    // PublicKeyDouble::verify                src/keys/public/double.rs:86-117
+    pub fn jjs_verify_double(ctx: *mut jjs_ctx, pk64: *const u8, sig96: *const u8, msg32: *const u8, n: usize,
+                             status: *mut u8, c32_or_null: *mut u8) -> c_int;
+    // PublicKeyVarGen::verify                src/keys/public/var_gen.rs:107-133
+    pub fn jjs_verify_vargen(ctx: *mut jjs_ctx, pk64: *const u8, sig64: *const u8, msg32: *const u8, n: usize,
+                             status: *mut u8, c32_or_null: *mut u8) -> c_int;
+    // multisig::aggregate_pk(..).verify(..)  src/multisig.rs:154-156, 393-429
+    pub fn jjs_verify_aggregate(ctx: *mut jjs_ctx, pks32: *const u8, offsets: *const u32, sig64: *const u8,
+                                msg32: *const u8, n: usize, status: *mut u8, c32_or_null: *mut u8,
+                                aggpk32_or_null: *mut u8) -> c_int;
+    // typed inputs: JubJubExtended coordinates, 160 bytes per point (variant 0: PK, R; 1: PK, PK', R, R'; 2: PK, gen, R)
+    pub fn jjs_verify_ext(ctx: *mut jjs_ctx, variant: c_int, points_ext160: *const u8, u32_: *const u8, msg32: *const u8,
+                          n: usize, status: *mut u8, c32_or_null: *mut u8) -> c_int;
+    pub fn jjs_verify_single_device(ctx: *mut jjs_ctx, device_index: c_int, d_pk32: *const u8, d_sig64: *const u8,
+                                    d_msg32: *const u8, n: usize, d_status: *mut u8, d_c32_or_null: *mut u8,
+                                    cuda_stream: *mut c_void) -> c_int;
+    // multisig::combine / verify_share over ragged sessions      src/multisig.rs:255-347, 366-387
+    pub fn jjs_multisig_combine(ctx: *mut jjs_ctx, pks32: *const u8, r32: *const u8, s32: *const u8, z32: *const u8,
+                                offsets: *const u32, msg32: *const u8, n: usize, share_ok_or_null: *mut u8, status: *mut u8,
+                                bad_index_or_null: *mut u32, sig64_or_null: *mut u8) -> c_int;
+    // .. jjs_verify_double_device, jjs_verify_vargen_device, jjs_verify_aggregate_device, jjs_challenge_only,
+    //    jjs_subgroup_check, jjs_sign_batch, jjs_sign_aggregate_batch, jjs_points_to_ext, jjs_profile_enable,
+    //    jjs_profile_collect, jjs_launch_count, jjs_status_bitmap_device: same pattern, see the header.
+}

@@ -94,3 +94,45 @@ def test_header_is_plain_c(tmp_path):
     import subprocess
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-c", os.path.join(ROOT, "tests", "cpp", "abi_c_check.c"),
                            "-o", str(tmp_path / "abi_c_check.o")])
+
+
+def _c_prototypes():
+    """{name: [parameter type strings]} of every jjs_* function declared in include/jjschnorr_b200.h"""
+    src = open(os.path.join(ROOT, "include", "jjschnorr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for ret, name, params in re.findall(r"\b(int|void|const char\*|uint64_t)\s+(jjs_[a-z_0-9]+)\s*\(([^)]*)\)\s*;", src):
+        out[name] = [" ".join(p.split()) for p in params.split(",")]
+    return out
+
+
+def test_rust_shim_matches_the_header():
+    """rust/ holds the shim of INTEGRATION.md as files; it cannot be compiled here, so at least its extern "C" block is
+    held against the C header: same function names, same number of parameters, pointer-ness and constness of each."""
+    import subprocess
+    import sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "extract_rust_shim.py"), "--check"])
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    ffi = re.sub(r"//[^\n]*", "", ffi)
+    protos = _c_prototypes()
+    rust = re.findall(r"pub fn (jjs_[a-z_0-9]+)\s*\(([^)]*)\)", ffi)
+    assert len(rust) >= 10
+    for name, params in rust:
+        assert name in protos, f"{name} is not declared in the header"
+        rparams = [p.strip() for p in params.split(",") if p.strip()]
+        cparams = protos[name]
+        assert len(rparams) == len(cparams), (name, rparams, cparams)
+        for rp, cp in zip(rparams, cparams):
+            rtype = rp.split(":", 1)[1].strip()
+            is_ptr = "*" in cp
+            assert rtype.startswith("*") == is_ptr, (name, rp, cp)
+            if is_ptr and "**" not in cp:
+                assert rtype.startswith("*const") == cp.startswith("const"), (name, rp, cp)
+            if not is_ptr:
+                assert {"size_t": "usize", "int": "c_int"}[cp.split()[0]] == rtype, (name, rp, cp)
+    # the status codes are the header's
+    hdr = open(os.path.join(ROOT, "include", "jjschnorr_b200.h")).read()
+    for cname in ("JJS_OK", "JJS_INVALID_SIGNATURE", "JJS_INVALID_POINT", "JJS_BYTES_ERROR"):
+        c_val = int(re.search(r"#define\s+%s\s+(\d+)" % cname, hdr).group(1))
+        r_val = int(re.search(r"pub const %s: u8 = (\d+);" % cname, ffi).group(1))
+        assert c_val == r_val, cname
