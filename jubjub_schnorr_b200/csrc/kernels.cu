@@ -114,11 +114,41 @@ __global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq*
     }
 }
 
-__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n,
-                                                     WireField msg, WireField usc, uint32_t* cwords, uint8_t* iflags) {
+// Work list of the hash and equation stages: the items that go on after decoding (verify_core.cuh, stage_item_ready).
+// The others are settled by their flags, and leaving them out keeps every lane of the two heavy kernels busy on
+// batches with many invalid items.  One warp ballot and one atomic per warp; also writes the scalar-range flag of every
+// item, clears its equation results and zeroes the challenge words of the items that are left out.
+__global__ void __launch_bounds__(BLOCK) k_work_list(int variant, const uint8_t* pflags, size_t n, WireField msg, WireField usc, bool require_valid_keys,
+                                                     uint8_t* iflags, uint8_t* eqflags, uint32_t* cwords, uint32_t* list, uint32_t* count) {
     size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= n) return;
-    stage_challenge(variant, pts_u, pts_v, pflags, n, item, msg, usc, cwords, iflags);
+    bool ready = false;
+    if (item < n) {
+        bool ok = stage_scalars_ok(msg, usc, item);
+        iflags[item] = ok ? IF_SCALARS_OK : 0;
+        ready = stage_item_ready(variant, pflags, n, item, ok, require_valid_keys);
+        eqflags[item] = 0;
+        if (variant == VAR_DOUBLE) eqflags[n + item] = 0;
+        if (!ready) {
+            uint4* c = reinterpret_cast<uint4*>(cwords + item * 8);
+            c[0] = make_uint4(0, 0, 0, 0);
+            c[1] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    uint32_t mask = __ballot_sync(0xffffffffu, ready);
+    if (mask == 0) return;
+    int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ready) list[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)item;
+}
+
+// thread t < *count hashes the challenge of item list[t]
+__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_challenge(int variant, const fq* pts_u, const fq* pts_v, size_t n, WireField msg,
+                                                                         const uint32_t* list, const uint32_t* count, uint32_t* cwords) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *count) return;
+    stage_challenge_hash(variant, pts_u, pts_v, n, list[t], msg, cwords);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_subgroup_check(WireField pts, size_t first, size_t count, int method, uint8_t* out, fq* tab,
@@ -128,32 +158,27 @@ __global__ void __launch_bounds__(BLOCK) k_subgroup_check(WireField pts, size_t 
     out[first + t] = subgroup_check(pts, first + t, method, tab + t, stride, T);
 }
 
-// thread t < neq * n : equation t / n of item t % n.  Signature points whose subgroup membership the equation did
-// not establish are appended to `rlist` (indices into the point arrays) for k_rtest.
-__global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags,
-                                                    const uint8_t* iflags, size_t n, size_t first, size_t count, WireField usc,
+// thread T = first + t < neq * *count : equation T % neq of item list[T / neq].  Signature points whose subgroup
+// membership the equation did not establish are appended to `rlist` (indices into the point arrays) for k_rtest.
+__global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n,
+                                                    size_t first, size_t count, const uint32_t* list, const uint32_t* lcount, WireField usc,
                                                     const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T,
                                                     uint32_t* rlist, uint32_t* rcount) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+    const int neq = variant == VAR_DOUBLE ? 2 : 1;
     size_t g = first + t;
-    int eq = (int)(g / n);
-    size_t item = g - (size_t)eq * n;
-    const int slots = variant_slots(variant);
-    bool ready = (iflags[item] & IF_SCALARS_OK) != 0;
-    for (int s = 0; s < slots; s++) ready = ready && (pflags[s * n + item] & PF_DECODED);
-    bool ok = false;
-    if (ready) {
-        bool need_r_test;
-        ok = stage_equation_item(variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
-                                 tab + t, tab + 36 * stride + t, stride, &need_r_test);
-        if (need_r_test) {
-            int pk_slot, r_slot, base_slot;
-            equation_slots(variant, eq, pk_slot, r_slot, base_slot);
-            rlist[atomicAdd(rcount, 1u)] = (uint32_t)((size_t)r_slot * n + item);
-        }
+    if (t >= count || g >= (size_t)neq * *lcount) return;
+    int eq = (int)(g % neq);
+    size_t item = list[g / neq];
+    bool need_r_test;
+    bool ok = stage_equation_item(variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
+                                  tab + t, tab + 36 * stride + t, stride, &need_r_test);
+    if (need_r_test) {
+        int pk_slot, r_slot, base_slot;
+        equation_slots(variant, eq, pk_slot, r_slot, base_slot);
+        rlist[atomicAdd(rcount, 1u)] = (uint32_t)((size_t)r_slot * n + item);
     }
-    eqflags[g] = ok ? 1 : 0;
+    eqflags[(size_t)eq * n + item] = ok ? 1 : 0;
 }
 
 // deferred subgroup tests: thread t < *rcount tests point rlist[t]
@@ -343,6 +368,7 @@ struct DeviceState {
     uint8_t *pflags = nullptr, *iflags = nullptr, *eqflags = nullptr;
     uint32_t* cwords = nullptr;
     uint32_t *rlist = nullptr, *rcount = nullptr;  // signature points awaiting the deferred subgroup test
+    uint32_t* eqlist = nullptr;                    // items that go on to the hash and equation kernels (k_work_list)
     // decoded signer keys of the aggregate-key path (grown on demand)
     fq *keys_u = nullptr, *keys_v = nullptr;
     uint8_t* kflags = nullptr;
@@ -364,12 +390,12 @@ struct DeviceState {
 struct Region {
     fq *pts_u, *pts_v, *tab;
     uint8_t *pflags, *iflags, *eqflags;
-    uint32_t *cwords, *rlist, *rcount;
+    uint32_t *cwords, *rlist, *rcount, *eqlist;   // rcount[0]: deferred subgroup tests, rcount[2]: length of the work list
     size_t cap;
 };
 inline Region region_of(const DeviceState& d, size_t first_item, size_t cap, int counter) {
     return Region{d.pts_u + 4 * first_item, d.pts_v + 4 * first_item, d.tab + first_item, d.pflags + 4 * first_item, d.iflags + first_item,
-                  d.eqflags + 2 * first_item, d.cwords + 8 * first_item, d.rlist + 2 * first_item, d.rcount + counter, cap};
+                  d.eqflags + 2 * first_item, d.cwords + 8 * first_item, d.rlist + 2 * first_item, d.rcount + counter, d.eqlist + 2 * first_item, cap};
 }
 inline Region region_whole(const DeviceState& d) { return region_of(d, 0, CHUNK_ITEMS, 0); }
 
@@ -440,7 +466,8 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaMalloc(&d.eqflags, 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.cwords, 32 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.rlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
-    JJS_CUDA(ctx, cudaMalloc(&d.rcount, 2 * sizeof(uint32_t)));
+    JJS_CUDA(ctx, cudaMalloc(&d.rcount, 4 * sizeof(uint32_t)));
+    JJS_CUDA(ctx, cudaMalloc(&d.eqlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * AGG_GROUP * 36 * TAB_THREADS));
     return JJS_SUCCESS;
 }
@@ -489,7 +516,21 @@ inline size_t sig_size(int variant) { return variant == VAR_DOUBLE ? 96 : 64; }
 // keys (and the var-gen generator) get their subgroup test in k_decode; signature points get it from the equation
 inline uint32_t key_slot_mask(int variant) { return variant == VAR_SINGLE ? 1u : 3u; }
 
-// Equation stage for a chunk of m <= R.cap items: the equations, then the deferred subgroup tests they asked for.
+// Hash stage for a chunk of m <= R.cap items: the work list, then the sponge of the items on it.
+int enqueue_challenges(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant, size_t m, const WireField& fmsg, const WireField& fu,
+                       cudaStream_t stream, bool require_valid_keys) {
+    StageTimer t1(ctx, d.device, 1, stream);
+    JJS_CUDA(ctx, cudaMemsetAsync(R.rcount + 2, 0, sizeof(uint32_t), stream));
+    k_work_list<<<blocks_for(m), BLOCK, 0, stream>>>(variant, R.pflags, m, fmsg, fu, require_valid_keys, R.iflags, R.eqflags, R.cwords, R.eqlist,
+                                                    R.rcount + 2);
+    k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, m, fmsg, R.eqlist, R.rcount + 2, R.cwords);
+    t1.stop(stream);
+    ctx->launches += 2;
+    return JJS_SUCCESS;
+}
+
+// Equation stage for a chunk of m <= R.cap items (after enqueue_challenges, whose work list it shares): the
+// equations, then the deferred subgroup tests they asked for.
 int enqueue_equations(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant, size_t m, const WireField& fu, cudaStream_t stream) {
     const int neq = variant == VAR_DOUBLE ? 2 : 1;
     Tables T = d.tables();
@@ -497,8 +538,8 @@ int enqueue_equations(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant
     JJS_CUDA(ctx, cudaMemsetAsync(R.rcount, 0, sizeof(uint32_t), stream));
     for (size_t first = 0; first < neq * m; first += R.cap) {
         size_t cnt = neq * m - first < R.cap ? neq * m - first : R.cap;
-        k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, R.iflags, m, first, cnt, fu, R.cwords, R.eqflags, R.tab,
-                                                         TAB_THREADS, T, R.rlist, R.rcount);
+        k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, first, cnt, R.eqlist, R.rcount + 2, fu, R.cwords,
+                                                         R.eqflags, R.tab, TAB_THREADS, T, R.rlist, R.rcount);
         ctx->launches++;
     }
     t3.stop(stream);
@@ -520,15 +561,14 @@ int run_chunk(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant, const 
     StageTimer t0(ctx, d.device, 0, stream);
     k_decode<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, 0, m, R.pts_u, R.pts_v, R.pflags, T, key_slot_mask(variant));
     t0.stop(stream);
-    StageTimer t1(ctx, d.device, 1, stream);
-    k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, fmsg, fu, R.cwords, R.iflags);
-    t1.stop(stream);
-    ctx->launches += 2;
+    ctx->launches++;
+    int rc = enqueue_challenges(ctx, d, R, variant, m, fmsg, fu, stream, !challenge_only);
+    if (rc) return rc;
     if (challenge_only) {
         JJS_CUDA(ctx, cudaMemcpyAsync(c_out, R.cwords, 32 * m, cudaMemcpyDeviceToDevice, stream));
         return JJS_SUCCESS;
     }
-    int rc = enqueue_equations(ctx, d, R, variant, m, fu, stream);
+    rc = enqueue_equations(ctx, d, R, variant, m, fu, stream);
     if (rc) return rc;
     StageTimer t4(ctx, d.device, 4, stream);
     k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(variant, R.pflags, R.iflags, R.eqflags, R.cwords, m, status, c_out);
@@ -688,16 +728,14 @@ int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, con
         k_aggregate<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, d.d_order, key_lo, m, d.pts_u, d.pts_v,
                                                         d.pflags, d_agg ? d_agg + 32 * off : nullptr, d.tab, TAB_THREADS, d.kcoef);
         t2.stop(stream);
-        StageTimer t1(ctx, d.device, 1, stream);
-        k_challenge<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
-        t1.stop(stream);
-        int rc2 = enqueue_equations(ctx, d, region_whole(d), VAR_SINGLE, m, fu, stream);
+        int rc2 = enqueue_challenges(ctx, d, region_whole(d), VAR_SINGLE, m, fmsg, fu, stream, true);
+        if (!rc2) rc2 = enqueue_equations(ctx, d, region_whole(d), VAR_SINGLE, m, fu, stream);
         if (rc2) return rc2;
         StageTimer t4(ctx, d.device, 4, stream);
         k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d_status + off,
                                                        d_c ? d_c + 32 * off : nullptr);
         t4.stop(stream);
-        ctx->launches += 6;
+        ctx->launches += 5;   // two decodes, the two aggregation kernels, finalize (the helpers count their own)
     }
     JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
@@ -793,12 +831,10 @@ int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, c
             StageTimer t0(ctx, d.device, 0, d.stream);
             k_decode_ext<<<blocks_for(slots * m), BLOCK, 0, d.stream>>>(b_pts, slots, m, d.pts_u, d.pts_v, d.pflags, key_slot_mask(variant));
             t0.stop(d.stream);
-            StageTimer t1(ctx, d.device, 1, d.stream);
-            k_challenge<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pts_u, d.pts_v, d.pflags, m, fmsg, fu, d.cwords, d.iflags);
-            t1.stop(d.stream);
+            if (enqueue_challenges(ctx, d, region_whole(d), variant, m, fmsg, fu, d.stream, true)) rc = JJS_ERR_CUDA;
             if (enqueue_equations(ctx, d, region_whole(d), variant, m, fu, d.stream)) rc = JJS_ERR_CUDA;
             k_finalize<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, b_st, c_out ? b_c : nullptr);
-            ctx->launches += 3;
+            ctx->launches += 2;   // decode, finalize
             cudaMemcpyAsync(status + off, b_st, m, cudaMemcpyDeviceToHost, d.stream);
             if (c_out) cudaMemcpyAsync(c_out + 32 * off, b_c, 32 * m, cudaMemcpyDeviceToHost, d.stream);
             cudaError_t e = cudaStreamSynchronize(d.stream);  // the staging buffer is reused by the next chunk
@@ -963,7 +999,7 @@ void free_device(DeviceState& d) {
     if (d.device < 0) return;
     cudaSetDevice(d.device);
     cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
-    cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords); cudaFree(d.rlist); cudaFree(d.rcount);
+    cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords); cudaFree(d.rlist); cudaFree(d.rcount); cudaFree(d.eqlist);
     cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c); cudaFree(d.s_bitmap);
     cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.kcoef); cudaFree(d.agg_stage); cudaFree(d.d_order);
     if (d.stream) cudaStreamDestroy(d.stream);

@@ -110,59 +110,82 @@ JJS_HD void stage_decode_ext(const WireField& f, size_t item, fq* out_u, fq* out
 }
 
 // ---- stage 2: challenge hash -------------------------------------------------------------------
-// pts_u / pts_v are [slots][n]; writes the challenge as 8 little-endian words and the scalar-range flag.
-JJS_HD void stage_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n, size_t item,
-                            const WireField& msg, const WireField& usc, uint32_t* c_out, uint8_t* item_flags) {
+// pts_u / pts_v are [slots][n].  The stage is split the way the kernels run it: (a) scalar range checks and the
+// decision whether the item goes on at all, (b) the sponge for the items that do.
+JJS_HD bool point_flags_valid(uint8_t f) { return (f & PF_TORSION_FREE) && !(f & PF_IDENTITY); }
+
+// BlsScalar::from_bytes(m) and JubJubScalar::from_bytes(u) succeed (reference src/signatures.rs:113, message decoding)
+JJS_HD bool stage_scalars_ok(const WireField& msg, const WireField& usc, size_t item) {
     uint32_t w[8];
+    wire_load(w, msg, item);
+    bool ok = !ge_q(w);
+    wire_load(w, usc, item);
+    return ok && fr_wire_is_canonical(w);
+}
+// An item goes on to the challenge hash and the equations iff every field decoded and -- unless the caller only wants
+// challenges -- its keys (and the var-gen generator) are valid: everything else is settled by the flags alone
+// (BytesError, or InvalidPoint from a key, both of which the reference reports before it hashes anything).
+JJS_HD bool stage_item_ready(int variant, const uint8_t* pflags, size_t n, size_t item, bool scalars_ok, bool require_valid_keys) {
+    const int slots = variant_slots(variant), nkeys = variant == VAR_SINGLE ? 1 : 2;
+    bool ready = scalars_ok;
+    for (int s = 0; s < slots; s++) ready = ready && (pflags[s * n + item] & PF_DECODED);
+    if (require_valid_keys)
+        for (int s = 0; s < nkeys; s++) ready = ready && point_flags_valid(pflags[s * n + item]);
+    return ready;
+}
+// the sponge of a ready item; writes the challenge as 8 little-endian words
+JJS_HD void stage_challenge_hash(int variant, const fq* pts_u, const fq* pts_v, size_t n, size_t item, const WireField& msg, uint32_t* c_out) {
+    uint32_t w[8], c[8];
     fq m;
     wire_load(w, msg, item);
-    bool ok = fq_from_wire(m, w);
-    wire_load(w, usc, item);
-    ok = ok && fr_wire_is_canonical(w);
-    const int slots = variant_slots(variant);
-    bool decoded = true;
-    for (int s = 0; s < slots; s++) decoded = decoded && (pflags[s * n + item] & PF_DECODED);
-    item_flags[item] = ok ? IF_SCALARS_OK : 0;
-    uint32_t c[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) c[i] = 0;
-    if (ok && decoded) {
-        Sponge sp;
-        if (variant == VAR_SINGLE) {  // [R.u, R.v, pk.u, pk.v, m]
-            sponge_start(sp, 5);
-            sponge_absorb(sp, pts_u[1 * n + item]);
-            sponge_absorb(sp, pts_v[1 * n + item]);
-            sponge_absorb(sp, pts_u[0 * n + item]);
-            sponge_absorb(sp, pts_v[0 * n + item]);
-            sponge_absorb(sp, m);
-        } else if (variant == VAR_DOUBLE) {  // [JJSCHDBL, R, R', pk, pk', m]
-            sponge_start(sp, 10);
-            fq tag;
-            fq_load_const(tag, JJS_C(DOUBLE_DOMAIN));
-            sponge_absorb(sp, tag);
-            sponge_absorb(sp, pts_u[2 * n + item]);
-            sponge_absorb(sp, pts_v[2 * n + item]);
-            sponge_absorb(sp, pts_u[3 * n + item]);
-            sponge_absorb(sp, pts_v[3 * n + item]);
-            sponge_absorb(sp, pts_u[0 * n + item]);
-            sponge_absorb(sp, pts_v[0 * n + item]);
-            sponge_absorb(sp, pts_u[1 * n + item]);
-            sponge_absorb(sp, pts_v[1 * n + item]);
-            sponge_absorb(sp, m);
-        } else {  // [R, pk, generator, m]
-            sponge_start(sp, 7);
-            sponge_absorb(sp, pts_u[2 * n + item]);
-            sponge_absorb(sp, pts_v[2 * n + item]);
-            sponge_absorb(sp, pts_u[0 * n + item]);
-            sponge_absorb(sp, pts_v[0 * n + item]);
-            sponge_absorb(sp, pts_u[1 * n + item]);
-            sponge_absorb(sp, pts_v[1 * n + item]);
-            sponge_absorb(sp, m);
-        }
-        sponge_squeeze_truncated(c, sp);
+    fq_from_wire(m, w);
+    Sponge sp;
+    if (variant == VAR_SINGLE) {  // [R.u, R.v, pk.u, pk.v, m]
+        sponge_start(sp, 5);
+        sponge_absorb(sp, pts_u[1 * n + item]);
+        sponge_absorb(sp, pts_v[1 * n + item]);
+        sponge_absorb(sp, pts_u[0 * n + item]);
+        sponge_absorb(sp, pts_v[0 * n + item]);
+        sponge_absorb(sp, m);
+    } else if (variant == VAR_DOUBLE) {  // [JJSCHDBL, R, R', pk, pk', m]
+        sponge_start(sp, 10);
+        fq tag;
+        fq_load_const(tag, JJS_C(DOUBLE_DOMAIN));
+        sponge_absorb(sp, tag);
+        sponge_absorb(sp, pts_u[2 * n + item]);
+        sponge_absorb(sp, pts_v[2 * n + item]);
+        sponge_absorb(sp, pts_u[3 * n + item]);
+        sponge_absorb(sp, pts_v[3 * n + item]);
+        sponge_absorb(sp, pts_u[0 * n + item]);
+        sponge_absorb(sp, pts_v[0 * n + item]);
+        sponge_absorb(sp, pts_u[1 * n + item]);
+        sponge_absorb(sp, pts_v[1 * n + item]);
+        sponge_absorb(sp, m);
+    } else {  // [R, pk, generator, m]
+        sponge_start(sp, 7);
+        sponge_absorb(sp, pts_u[2 * n + item]);
+        sponge_absorb(sp, pts_v[2 * n + item]);
+        sponge_absorb(sp, pts_u[0 * n + item]);
+        sponge_absorb(sp, pts_v[0 * n + item]);
+        sponge_absorb(sp, pts_u[1 * n + item]);
+        sponge_absorb(sp, pts_v[1 * n + item]);
+        sponge_absorb(sp, m);
     }
+    sponge_squeeze_truncated(c, sp);
 #pragma unroll
     for (int i = 0; i < 8; i++) c_out[item * 8 + i] = c[i];
+}
+// Both halves for one item (what the work-list kernel and the hash kernel do together).  Returns whether the item is ready;
+// the challenge words of an item that is not are zero.
+JJS_HD bool stage_challenge(int variant, const fq* pts_u, const fq* pts_v, const uint8_t* pflags, size_t n, size_t item,
+                            const WireField& msg, const WireField& usc, uint32_t* c_out, uint8_t* item_flags, bool require_valid_keys = true) {
+    bool ok = stage_scalars_ok(msg, usc, item);
+    item_flags[item] = ok ? IF_SCALARS_OK : 0;
+    bool ready = stage_item_ready(variant, pflags, n, item, ok, require_valid_keys);
+    if (ready) stage_challenge_hash(variant, pts_u, pts_v, n, item, msg, c_out);
+    else
+        for (int i = 0; i < 8; i++) c_out[item * 8 + i] = 0;
+    return ready;
 }
 
 // ---- subgroup membership of one wire-encoded point, by either method (cross-check hook) ------------
@@ -247,7 +270,6 @@ JJS_HD void equation_slots(int variant, int eq, int& pk_slot, int& r_slot, int& 
     else if (variant == VAR_DOUBLE) { pk_slot = eq; r_slot = 2 + eq; base_slot = -1; }
     else { pk_slot = 0; r_slot = 2; base_slot = 1; }
 }
-JJS_HD bool point_flags_valid(uint8_t f) { return (f & PF_TORSION_FREE) && !(f & PF_IDENTITY); }
 JJS_HD bool stage_equation_item(int variant, int eq, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n, size_t item, const niels* fb,
                                 const WireField& usc, const uint32_t* c_words, fq* tabA, fq* tabB, size_t stride, bool* need_r_test) {
     int pk_slot, r_slot, base_slot;

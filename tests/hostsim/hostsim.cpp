@@ -186,8 +186,7 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
         stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1, kc.data());
         memcpy(agg_out + 32 * i, w, 32);
         stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables, false);
-        stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
-        bool all = (itf[i] & IF_SCALARS_OK) && (pf[i] & PF_DECODED) && (pf[n + i] & PF_DECODED);
+        bool all = stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
         if (all && equation_with_rtest(VAR_SINGLE, 0, pu.data(), pv.data(), pf.data(), n, i, fu, cw.data(), tab.data())) itf[i] |= IF_EQ0_OK;
         status[i] = stage_status(VAR_SINGLE, pf.data(), itf[i], n, i);
         if (status[i] <= 1) memcpy(c_out + 32 * i, &cw[8 * i], 32); else memset(c_out + 32 * i, 0, 32);
@@ -226,9 +225,7 @@ void hs_verify_ext(int variant, const uint8_t* pts, const uint8_t* u32, const ui
             stage_decode_ext(WireField{pts + 160 * s, (uint32_t)(160 * slots)}, i, pu.data(), pv.data(), pf.data(), s * n + i,
                              s < (variant == VAR_SINGLE ? 1 : 2));
     for (size_t i = 0; i < n; i++) {
-        stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
-        bool all = (itf[i] & IF_SCALARS_OK);
-        for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);
+        bool all = stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
         if (all) {
             for (int eq = 0; eq < (variant == VAR_DOUBLE ? 2 : 1); eq++)
                 if (equation_with_rtest(variant, eq, pu.data(), pv.data(), pf.data(), n, i, fu, cw.data(), tab.data())) itf[i] |= eq ? IF_EQ1_OK : IF_EQ0_OK;
@@ -286,10 +283,10 @@ void hs_verify(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t
     std::vector<uint32_t> cw(8 * n);
     for (int s = 0; s < slots; s++)
         for (size_t i = 0; i < n; i++) stage_decode(f[s], i, pu.data(), pv.data(), pf.data(), s * n + i, g_tables, s < (variant == VAR_SINGLE ? 1 : 2));
-    for (size_t i = 0; i < n; i++) stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
+    std::vector<uint8_t> ready(n);
+    for (size_t i = 0; i < n; i++) ready[i] = stage_challenge(variant, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
     for (size_t i = 0; i < n; i++) {
-        bool all = (itf[i] & IF_SCALARS_OK);
-        for (int s = 0; s < slots; s++) all = all && (pf[s * n + i] & PF_DECODED);
+        bool all = ready[i];
         if (all) {
             for (int eq = 0; eq < (variant == VAR_DOUBLE ? 2 : 1); eq++)
                 if (equation_with_rtest(variant, eq, pu.data(), pv.data(), pf.data(), n, i, fu, cw.data(), tab.data())) itf[i] |= eq ? IF_EQ1_OK : IF_EQ0_OK;
