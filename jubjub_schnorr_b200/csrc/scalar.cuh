@@ -29,6 +29,37 @@ JJS_HD void fr_mul(uint32_t* out, const uint32_t* a, const uint32_t* b, int nbit
     mul_wide(t, a, b);
     fr_reduce_wide(out, t, nbits);
 }
+// out = a * b mod r for a < 2^128 (its four low limbs are used) and b < r, by Barrett reduction: with
+// x = a b < 2^380,  q = ((x >> 248) * floor(2^380 / r)) >> 132  is floor(x / r) or up to two less, so x - q r < 3 r
+// and two conditional subtractions finish.  Three wide products on the multiply pipe replace the 384 shift-and-subtract
+// steps of fr_reduce_wide (the equation kernel computes rho * u this way, once per equation, with every warp of the
+// SM in that phase at the same time).
+JJS_HD void fr_mul_short(uint32_t* out, const uint32_t* a4, const uint32_t* b8) {
+    constexpr uint32_t MU[5] = {0x83f0476au, 0x1c5aee5bu, 0xff6f1bbeu, 0x1aa84a76u, 0x1u};  // floor(2^380 / r)
+    uint32_t a[8], x[16], x1[8], mu[8], t[16], q[8], ord[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = i < 4 ? a4[i] : 0u; mu[i] = i < 5 ? MU[i] : 0u; ord[i] = JJS_C(R_ORDER)[i]; }
+    mul_wide(x, a, b8);
+    // x1 = x >> 248 (248 = 7 * 32 + 24): five limbs
+#pragma unroll
+    for (int i = 0; i < 8; i++) x1[i] = i < 5 ? ((x[7 + i] >> 24) | (x[8 + i] << 8)) : 0u;
+    mul_wide(t, x1, mu);
+    // q = t >> 132 (132 = 4 * 32 + 4): four limbs
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = i < 4 ? ((t[4 + i] >> 4) | (t[5 + i] << 28)) : 0u;
+    mul_wide(t, q, ord);
+    // rem = x - q r over nine limbs (the true value is below 3 r < 2^254)
+    uint32_t rem[8], s[8];
+    sub8(rem, x, t);
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        uint32_t borrow = sub8(s, rem, ord);
+#pragma unroll
+        for (int i = 0; i < 8; i++) rem[i] = borrow ? rem[i] : s[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = rem[i];
+}
 JJS_HD void fr_sub(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // a, b < r
     uint32_t d[8], ord[8], e[8];
 #pragma unroll

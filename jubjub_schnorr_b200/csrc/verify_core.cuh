@@ -239,7 +239,7 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
         varbase_table_build(tabB, stride, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
         straus2<33>(acc, tabA, tabB, stride, dT, dR);
         uint32_t ru[8];
-        fr_mul(ru, rho, u, 384);  // |rho| * u < 2^126 * 2^252
+        fr_mul_short(ru, rho, u);  // |rho| * u mod r,  |rho| < 2^126
         ext ub, sum;
         fixedbase_mul(ub, fb, ru);
         pniels nb;

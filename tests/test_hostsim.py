@@ -185,6 +185,22 @@ def test_pipeline_twin_on_adversarial_batches(L, vi, kind):
     assert np.array_equal(hc, c) and np.array_equal(st, exp)
 
 
+def test_scalar_products_mod_r(L):
+    """rho * u mod r by Barrett reduction (rho < 2^128) and the general bit-serial product, against big integers."""
+    rnd = random.Random(9)
+    r = o.R_ORDER
+    out = (C.c_uint32 * 8)()
+    cases = [(0, 0), (1, r - 1), ((1 << 126) - 1, r - 1), ((1 << 128) - 1, r - 1), ((1 << 127) + 12345, 1), (1 << 125, r // 2)]
+    cases += [(rnd.getrandbits(126), rnd.randrange(r)) for _ in range(3000)]
+    for a, b in cases:
+        L.hs_fr_mul_short(arr(a, 4), arr(b), out)
+        assert val(out) == a * b % r, (hex(a), hex(b))
+    for _ in range(200):
+        a, b = rnd.randrange(r), rnd.randrange(r)
+        L.hs_fr_mul(arr(a), arr(b), out)
+        assert val(out) == a * b % r
+
+
 def test_half_size_decomposition(L):
     """tau == rho * c (mod r) with |tau| < 2^130, 0 < |rho| < 2^126, the digits recompose them, and rho is odd for
     nearly every challenge (what lets the equation stand in for the subgroup test of R)."""
