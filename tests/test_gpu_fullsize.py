@@ -152,3 +152,21 @@ def test_argument_errors_are_reported_not_fatal(bv):
     dev = (C.c_int * 1)(99)
     assert lib.jjs_init(dev, 1, C.byref(ctx)) == -1 and b"not present" in lib.jjs_last_error(ctx)
     lib.jjs_destroy(ctx)
+
+
+def test_one_context_over_two_devices():
+    """Single-process sharding of the host entry points (contiguous shards, one set of streams per device, shards
+    starting on a bitmap word).  Needs two GPUs; skipped on a one-GPU box (tools/check_two_devices.py is the same check)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from jubjub_schnorr_b200 import BatchVerifier
+    from jubjub_schnorr_b200 import workload as wl
+    with BatchVerifier([0]) as g:
+        batches = [(v, n) + tuple(wl.make_batch(g, v, n, 0.2, seed=11 * v + n)[:4]) for v, n in ((0, 300_001), (1, 70_001), (2, 65_537), (0, 33), (0, 1))]
+    with BatchVerifier([0, 1]) as bv:
+        for v, n, pk, sig, msg, exp in batches:
+            st, _ = {0: bv.verify_single, 1: bv.verify_double, 2: bv.verify_vargen}[v](pk, sig, msg, True)
+            assert np.array_equal(st, exp), (v, n)
+            if v == 0:
+                assert np.array_equal(bv.unpack_bitmap(bv.verify_batch(pk, sig, msg), n), exp == 0), n
