@@ -802,46 +802,65 @@ int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, c
     if (!pts || !u32 || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     const int slots = variant_slots(variant);
     const size_t g = ctx->dev.size(), per = (n + g - 1) / g;
-    int rc = JJS_SUCCESS;
-    for (size_t k = 0; k < g && rc == JJS_SUCCESS; k++) {
+    // Same structure as run_host: every device gets a contiguous shard, staged whole on the device; the shard is cut into
+    // slices (a short first one) whose H2D copies run on the copy stream while earlier slices are being verified on the
+    // two alternating compute streams / scratch halves.  Nothing is synchronised before every device has its work.
+    for (size_t k = 0; k < g; k++) {
         size_t lo = k * per, hi = lo + per < n ? lo + per : n;
         if (lo >= hi) break;
         DeviceState& d = ctx->dev[k];
-        rc = ensure_scratch(ctx, d);
-        if (rc) break;
-        cudaSetDevice(d.device);
-        Tables T = d.tables();
-        for (size_t off = lo; off < hi && rc == JJS_SUCCESS; off += CHUNK_ITEMS) {
-            size_t m = hi - off < CHUNK_ITEMS ? hi - off : CHUNK_ITEMS;
-            size_t need = m * (160 * (size_t)slots + 32 + 32 + 1 + 32);
-            if (need > d.agg_stage_bytes) {
-                cudaStreamSynchronize(d.stream);
-                cudaFree(d.agg_stage);
-                d.agg_stage = nullptr;
-                d.agg_stage_bytes = 0;
-                cudaError_t e = cudaMalloc(&d.agg_stage, need);
-                if (e != cudaSuccess) { rc = fail(ctx, JJS_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
-                d.agg_stage_bytes = need;
-            }
-            uint8_t *b_pts = d.agg_stage, *b_u = b_pts + 160 * (size_t)slots * m, *b_msg = b_u + 32 * m, *b_c = b_msg + 32 * m, *b_st = b_c + 32 * m;
-            cudaMemcpyAsync(b_pts, pts + 160 * (size_t)slots * off, 160 * (size_t)slots * m, cudaMemcpyHostToDevice, d.stream);
-            cudaMemcpyAsync(b_u, u32 + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
-            cudaMemcpyAsync(b_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
-            WireField fmsg{b_msg, 32}, fu{b_u, 32};
-            StageTimer t0(ctx, d.device, 0, d.stream);
-            k_decode_ext<<<blocks_for(slots * m), BLOCK, 0, d.stream>>>(b_pts, slots, m, d.pts_u, d.pts_v, d.pflags, key_slot_mask(variant));
-            t0.stop(d.stream);
-            if (enqueue_challenges(ctx, d, region_whole(d), variant, m, fmsg, fu, d.stream, true)) rc = JJS_ERR_CUDA;
-            if (enqueue_equations(ctx, d, region_whole(d), variant, m, fu, d.stream)) rc = JJS_ERR_CUDA;
-            k_finalize<<<blocks_for(m), BLOCK, 0, d.stream>>>(variant, d.pflags, d.iflags, d.eqflags, d.cwords, m, b_st, c_out ? b_c : nullptr);
-            ctx->launches += 2;   // decode, finalize
-            cudaMemcpyAsync(status + off, b_st, m, cudaMemcpyDeviceToHost, d.stream);
-            if (c_out) cudaMemcpyAsync(c_out + 32 * off, b_c, 32 * m, cudaMemcpyDeviceToHost, d.stream);
-            cudaError_t e = cudaStreamSynchronize(d.stream);  // the staging buffer is reused by the next chunk
-            if (e != cudaSuccess) rc = fail(ctx, JJS_ERR_CUDA, "typed verify failed: %s", cudaGetErrorString(e));
+        int rc = ensure_scratch(ctx, d);
+        if (rc) return rc;
+        JJS_CUDA(ctx, cudaSetDevice(d.device));
+        const size_t m = hi - lo, ptw = 160 * (size_t)slots;
+        const size_t need = m * (ptw + 32 + 32 + 32 + 1);
+        if (need > d.agg_stage_bytes) {
+            JJS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+            cudaFree(d.agg_stage);
+            d.agg_stage = nullptr;
+            d.agg_stage_bytes = 0;
+            JJS_CUDA(ctx, cudaMalloc(&d.agg_stage, need));
+            d.agg_stage_bytes = need;
         }
+        uint8_t *b_pts = d.agg_stage, *b_u = b_pts + ptw * m, *b_msg = b_u + 32 * m, *b_c = b_msg + 32 * m, *b_st = b_c + 32 * m;
+        const bool serial = ctx->profile;
+        size_t j = 0;
+        for (size_t off = 0; off < m; j++) {
+            size_t want = j == 0 ? SUB_CHUNK / 4 : SUB_CHUNK;
+            size_t cnt = m - off < want ? m - off : want;
+            JJS_CUDA(ctx, cudaMemcpyAsync(b_pts + ptw * off, pts + ptw * (lo + off), ptw * cnt, cudaMemcpyHostToDevice, d.copy_stream));
+            JJS_CUDA(ctx, cudaMemcpyAsync(b_u + 32 * off, u32 + 32 * (lo + off), 32 * cnt, cudaMemcpyHostToDevice, d.copy_stream));
+            JJS_CUDA(ctx, cudaMemcpyAsync(b_msg + 32 * off, msg + 32 * (lo + off), 32 * cnt, cudaMemcpyHostToDevice, d.copy_stream));
+            JJS_CUDA(ctx, cudaEventRecord(d.copied, d.copy_stream));
+            cudaStream_t cs = serial ? d.stream : d.sub[j & 1];
+            JJS_CUDA(ctx, cudaStreamWaitEvent(cs, d.copied, 0));
+            Region R = region_of(d, (j & 1) * SUB_ITEMS, SUB_ITEMS, (int)(j & 1));
+            WireField fmsg{b_msg + 32 * off, 32}, fu{b_u + 32 * off, 32};
+            StageTimer t0(ctx, d.device, 0, cs);
+            k_decode_ext<<<blocks_for(slots * cnt), BLOCK, 0, cs>>>(b_pts + ptw * off, slots, cnt, R.pts_u, R.pts_v, R.pflags, key_slot_mask(variant));
+            t0.stop(cs);
+            rc = enqueue_challenges(ctx, d, R, variant, cnt, fmsg, fu, cs, true);
+            if (!rc) rc = enqueue_equations(ctx, d, R, variant, cnt, fu, cs);
+            if (rc) return rc;
+            k_finalize<<<blocks_for(cnt), BLOCK, 0, cs>>>(variant, R.pflags, R.iflags, R.eqflags, R.cwords, cnt, b_st + off, c_out ? b_c + 32 * off : nullptr);
+            ctx->launches += 2;   // decode, finalize
+            off += cnt;
+        }
+        if (!serial)
+            for (int q = 0; q < 2; q++) {
+                JJS_CUDA(ctx, cudaEventRecord(d.join[q], d.sub[q]));
+                JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.join[q], 0));
+            }
+        JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, b_st, m, cudaMemcpyDeviceToHost, d.stream));
+        if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + 32 * lo, b_c, 32 * m, cudaMemcpyDeviceToHost, d.stream));
     }
-    return rc;
+    for (size_t k = 0; k < g; k++) {
+        JJS_CUDA(ctx, cudaSetDevice(ctx->dev[k].device));
+        cudaError_t e = cudaStreamSynchronize(ctx->dev[k].stream);
+        if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "typed verify failed: %s", cudaGetErrorString(e));
+    }
+    JJS_CUDA(ctx, cudaGetLastError());
+    return JJS_SUCCESS;
 }
 
 // multisig::combine for n ragged sessions (host buffers, device 0); chunks hold at most 2^20 participants
