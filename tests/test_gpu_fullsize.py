@@ -164,7 +164,9 @@ def test_one_context_over_two_devices():
     from jubjub_schnorr_b200 import workload as wl
     with BatchVerifier([0]) as g:
         batches = [(v, n) + tuple(wl.make_batch(g, v, n, 0.2, seed=11 * v + n)[:4]) for v, n in ((0, 300_001), (1, 70_001), (2, 65_537), (0, 33), (0, 1))]
+        pts, u, tmsg, texp = wl.make_typed_single_batch(g, 150_001, 0.10)
     with BatchVerifier([0, 1]) as bv:
+        assert np.array_equal(bv.verify_ext(0, pts, u, tmsg), texp)
         for v, n, pk, sig, msg, exp in batches:
             st, _ = {0: bv.verify_single, 1: bv.verify_double, 2: bv.verify_vargen}[v](pk, sig, msg, True)
             assert np.array_equal(st, exp), (v, n)

@@ -9,6 +9,7 @@ with BatchVerifier([0]) as g:
     for variant, n in ((0, 300001), (1, 70001), (2, 65537), (0, 33), (0, 1)):
         data[(variant, n)] = wl.make_batch(g, variant, n, 0.2, seed=variant * 7 + n)
     agg = wl.make_aggregate_batch(g, 50001, 0.05, seed=5)
+    typed = wl.make_typed_single_batch(g, 150001, 0.10)
 with BatchVerifier([0, 1]) as bv:
     assert bv._lib.jjs_device_count(bv._ctx) == 2
     for (variant, n), (pk, sig, msg, exp, _) in data.items():
@@ -23,4 +24,8 @@ with BatchVerifier([0, 1]) as bv:
     st = bv.verify_aggregate(pks, off, sig, msg)
     assert np.array_equal(st, exp)
     print("ok aggregate")
+    pts, u, msg, exp = typed
+    for rep in range(2):
+        assert np.array_equal(bv.verify_ext(0, pts, u, msg), exp)
+    print("ok typed")
 print("multi-device ok")
