@@ -9,19 +9,29 @@ signatures with 10 % invalid items per GPU; weak scaling, every rank owns its ow
             CUDA events on the launching stream, max over ranks)
   e2e       same metric through the host-buffer C ABI call a reference user would make (pinned host buffers,
             H2D + D2H inside the timed region)
+  e2e_pageable  the same call from ordinary (pageable) numpy memory, what a Rust Vec<u8> is
   roofline  dominant kernel against the measured INT32-multiply peak (profiles/r01_microbench_int.json); this
-            path is bound by the integer multiply pipe, not by HBM or tensor cores
-  cpu_baseline  the oracle's C port of the reference algorithm on the host cores, bounded sample
---impl reference times that CPU port (the reference is Rust and cannot be built here).
+            path is bound by the integer multiply pipe, not by HBM or tensor cores.
+            frac counts the CANONICAL algorithm's multiplies (SURVEY 8(d) contract); roofline.executed counts the
+            IMAD.WIDE the kernels really execute (ncu, profiles/r*_executed_mac32.json) and is the pipe-efficiency figure
+  strong_2p24   BASELINE.json configs[4]: a 2^24-item half single / half double batch through ONE context over all N
+            GPUs and ONE jjs_verify_mixed host call (rank 0; under torchrun the other ranks wait on a CPU barrier)
+  cpu_baseline  BASELINE.json configs[0]: 2^16 valid single signatures through the oracle's C port of the reference
+            algorithm on all host threads
+--impl reference times that CPU port on a bounded sample of the GPU arm's workload (same invalid mix; the reference is
+Rust and cannot be built here).
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
 import sys
 import time
+
+import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -90,12 +100,15 @@ def host_threads() -> int:
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle's C port of the reference algorithm (kind 'port'), all host threads, bounded sample."""
+    """CPU arm: the oracle's C port of the reference algorithm (kind 'port'), all host threads.  Each step verifies a bounded
+    sample of the GPU arm's workload: oracle-generated valid items invalidated by the SAME routine, classes and fraction as the
+    GPU arm's batches (jubjub_schnorr_b200.workload.invalidate: plain numpy, no kernel involved)."""
     if rank != 0:
         return
     if not args.log2n:
         args.log2n = 24 if args.workload == "mixed5" else 20
     import numpy as np
+    from jubjub_schnorr_b200 import workload as wl
     from oracle import c_oracle as co
     co.build()
     threads = host_threads()
@@ -105,18 +118,22 @@ def run_reference(args, rank, world):
     per = sample // len(kinds)
     jobs = []
     for kind in kinds:
-        k = max(1, int(round((0.05 if "aggregate" in args.workload or args.workload == "mixed4" else 0.10) * per)))
+        frac = 0.05 if (kind == "aggregate" or args.workload == "mixed4") else 0.10
         if kind == "aggregate":
             signers = np.random.default_rng(1).choice(np.array([2, 3, 4], dtype=np.uint32), size=per)
             pks, off, sig, msg = co.gen_aggregate(0xB200, signers, threads=threads)
+            k = max(1, int(round(frac * per)))
             sig[:k, 0] ^= 1
-            jobs.append((lambda pks=pks, off=off, sig=sig, msg=msg: co.verify_aggregate(pks, off, sig, msg, threads=threads)[0], k))
+            expected = np.zeros(per, dtype=np.uint8)
+            expected[:k] = 1
+            jobs.append((lambda pks=pks, off=off, sig=sig, msg=msg: co.verify_aggregate(pks, off, sig, msg, threads=threads)[0], expected))
         else:
+            variant = {"single": wl.SINGLE, "double": wl.DOUBLE, "vargen": wl.VARGEN}[kind]
             gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
             ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
             pk, sig, msg = gen(0xB200, per, threads=threads)
-            sig[:k, 0] ^= 1  # tampered u, same invalid proportion as the GPU workload
-            jobs.append((lambda ver=ver, pk=pk, sig=sig, msg=msg: ver(pk, sig, msg, threads=threads)[0], k))
+            pk, sig, msg, expected, _ = wl.invalidate(variant, pk, sig, msg, frac, seed=0xB200)
+            jobs.append((lambda ver=ver, pk=pk, sig=sig, msg=msg: ver(pk, sig, msg, threads=threads)[0], expected))
     sample = per * len(kinds)
     for _ in range(args.warmup):
         for fn, _ in jobs:
@@ -125,14 +142,15 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         results = [fn() for fn, _ in jobs]
     dt = time.perf_counter() - t0
-    assert all(int((st != 0).sum()) == k for st, (_, k) in zip(results, jobs))
+    assert all(np.array_equal(st, exp) for st, (_, exp) in zip(results, jobs)), "CPU port disagrees with the constructed expectation"
     value = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs)",
-        "data": "synthetic", "config": workload_config(args, sample_items=sample),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} {args.workload} items per step, oracle/jjs_oracle.c (reference algorithm restated in C; the Rust crate cannot be built here)"},
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "mixed5" else "weak", "vs_baseline": None,
+        "dtype": "u64 (4x64-bit Montgomery limbs)", "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "per_thread": value / threads, "nproc": os.cpu_count(),
+                         "sample": f"{sample} items per step drawn like the GPU arm's batch ({args.workload}: same generator classes and invalid fraction), "
+                                   "oracle/jjs_oracle.c (reference algorithm restated in C; the Rust crate cannot be built here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,7 +189,7 @@ def plan_parts(args, n_gpus_total):
     raise SystemExit("unknown workload")
 
 
-def workload_config(args, sample_items=None):
+def workload_config(args):
     n = 1 << args.log2n
     desc = {
         "single": f"2^{args.log2n} single Schnorr signatures per GPU, 10% tampered/invalid",
@@ -184,8 +202,6 @@ def workload_config(args, sample_items=None):
     cfg = {"workload": f"{desc} (BASELINE.json configs[{CONFIG_INDEX[args.workload]}])", "items_per_gpu": n if args.workload != "mixed5" else n // args.gpus,
            "l2_policy": "inputs (>=128 MiB) plus >1 GiB of per-step scratch exceed the 126 MB L2; no explicit flush",
            "parallelism": f"{args.gpus} independent shard(s), no collective on the data path"}
-    if sample_items is not None:
-        cfg["cpu_sample_items"] = sample_items
     return cfg
 
 
@@ -193,7 +209,6 @@ class Part:
     """One homogeneous sub-batch resident on one device."""
 
     def __init__(self, bv, wl, kind, n, frac, seed, rank, dev_index, torch):
-        import numpy as np
         self.kind, self.n, self.bv, self.dev_index, self.torch = kind, n, bv, dev_index, torch
         self.variant = {"single": wl.SINGLE, "double": wl.DOUBLE, "vargen": wl.VARGEN, "aggregate": None}[kind]
         if kind == "aggregate":
@@ -223,7 +238,18 @@ class Part:
     def pin(self):
         t = self.torch
         self.h = [t.from_numpy(x).pin_memory() for x in (self.pk, self.sig, self.msg)]
+        self.h_off = t.from_numpy(self.off.view(np.int32)).pin_memory() if self.off is not None else None
         self.h_status = t.empty(self.n, dtype=t.uint8).pin_memory()
+        self.p_status = np.empty(self.n, dtype=np.uint8)     # pageable result buffer
+
+    def host_part(self, pageable=False):
+        """One jjs_part of the mixed host call: pinned torch tensors, or the pageable numpy arrays the batch was made in."""
+        kind = 3 if self.off is not None else self.variant
+        if pageable:
+            return (kind, self.pk.ctypes.data, self.off.ctypes.data if self.off is not None else None, self.sig.ctypes.data, self.msg.ctypes.data, self.n,
+                    self.p_status.ctypes.data, None, None, None)
+        return (kind, self.h[0].data_ptr(), self.h_off.data_ptr() if self.h_off is not None else None, self.h[1].data_ptr(), self.h[2].data_ptr(), self.n,
+                self.h_status.data_ptr(), None, None, None)
 
     def step_device(self):
         if self.off is None:
@@ -232,13 +258,6 @@ class Part:
         else:
             self.bv.verify_aggregate_device(self.d[0].data_ptr(), self.d[3].data_ptr(), self.off, self.d[1].data_ptr(), self.d[2].data_ptr(), self.n,
                                             self.d_status.data_ptr(), self.d_c.data_ptr(), None, stream=self.stream.cuda_stream, device_index=self.dev_index)
-
-    def step_host(self, bv_host):
-        if self.off is None:
-            bv_host.verify_host_ptr(self.variant, self.h[0].data_ptr(), self.h[1].data_ptr(), self.h[2].data_ptr(), self.n, self.h_status.data_ptr(), None)
-        else:
-            st = bv_host.verify_aggregate(self.h[0].numpy(), self.off, self.h[1].numpy(), self.h[2].numpy())
-            self.h_status.numpy()[:] = st
 
     def canonical_mac32(self):
         """{stage: canonical MAC32 of this part for one step}"""
@@ -274,6 +293,8 @@ def main():
     ap.add_argument("--log2n", type=int, default=0, help="log2 of the items per GPU (mixed5: of the whole job); default 20 (mixed5: 24)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 2^24 strong-scaling sub-record")
+    ap.add_argument("--strong-log2n", type=int, default=24)
     args = ap.parse_args()
     if not args.log2n:
         args.log2n = 24 if args.workload == "mixed5" else 20
@@ -378,26 +399,29 @@ def main():
     value = items_per_device * n_gpus_total * args.steps / (ms_dev * 1e-3)
 
     # ---- end to end through the host-buffer C ABI ("e2e") ---------------------------------------------------
-    # the host entry points shard one host batch over the context's devices themselves
+    # ONE jjs_verify_mixed call per step carries every part; the library shards each part over the context's devices itself
     host_parts = shards[0] if len(devices) == 1 else [Part(bv, wl, kind, n * len(devices), frac, 0xE2E + 17 * j, rank, 0, torch) for j, (kind, n, frac) in enumerate(plan)]
     for p in host_parts:
         p.pin()
 
-    def step_host():
+    def time_host(pageable):
+        tuples = [p.host_part(pageable) for p in host_parts]
+        for _ in range(max(1, args.warmup - 1)):
+            bv.verify_mixed_ptr(tuples)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            bv.verify_mixed_ptr(tuples)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
         for p in host_parts:
-            p.step_host(bv)
+            got = p.p_status if pageable else p.h_status.numpy()
+            assert np.array_equal(got, p.expected), f"host-path statuses differ from the constructed expectation ({p.kind}, pageable={pageable})"
+        return dt
 
-    for _ in range(max(1, args.warmup - 1)):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    for p in host_parts:
-        assert np.array_equal(p.h_status.numpy(), p.expected), f"host-path statuses differ from the constructed expectation ({p.kind})"
+    e2e_s = time_host(False)
     e2e_value = items_per_device * n_gpus_total * args.steps / e2e_s
+    pageable_s = time_host(True)
     h2d = sum(p.h2d for p in host_parts)
     d2h = sum(p.n for p in host_parts)
 
@@ -411,54 +435,174 @@ def main():
     step_achieved = step_mac32 * n_gpus_total / (ms_dev / args.steps * 1e-3) / 1e12 / n_gpus_total
     bytes_in = sum(p.h2d for p in shards[0])
     hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    units = {"decode": sum(p.n * SLOTS.get(p.kind, 1) for p in shards[0]), "challenge": sum(p.n_equation_items for p in shards[0]),
+             "equation": sum(p.n_equation_items * NEQ.get(p.kind, 1) for p in shards[0]), "aggregate": sum(p.n for p in shards[0] if p.kind == "aggregate")}
     traffic = None
     try:  # DRAM bytes of the dominant kernel per step, from the committed ncu capture (bytes per unit x units in this step)
-        import glob
         traffic_file = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))[-1]   # newest capture
         tr = json.load(open(traffic_file))["kernels"]["k_" + dom]
-        units = {"decode": sum(p.n * SLOTS.get(p.kind, 1) for p in shards[0]), "challenge": sum(p.n for p in shards[0]),
-                 "equation": sum(p.n * NEQ.get(p.kind, 1) for p in shards[0]), "aggregate": sum(p.n for p in shards[0] if p.kind == "aggregate")}[dom]
-        traffic = tr["dram_bytes_per_unit"] * units
+        traffic = tr["dram_bytes_per_unit"] * {"decode": units["decode"], "challenge": sum(p.n for p in shards[0]),
+                                               "equation": sum(p.n * NEQ.get(p.kind, 1) for p in shards[0]), "aggregate": units["aggregate"]}[dom]
+    except Exception:
+        pass
+    # executed multiplies: IMAD.WIDE / IMAD.HI thread instructions per unit of each kernel, counted by ncu on this build
+    # (profiles/r*_executed_mac32.json, made by tools/ncu_executed.py from the source pages of the committed captures)
+    executed = None
+    try:
+        ex_file = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_executed_mac32.json")))[-1]
+        ex = json.load(open(ex_file))["per_unit"]
+        per_stage = {"decode": 0.0, "challenge": 0.0, "equation": 0.0}
+        for p in shards[0]:
+            if p.kind not in ex:
+                raise KeyError(p.kind)
+            per_stage["decode"] += ex[p.kind]["k_decode"] * p.n * SLOTS[p.kind]
+            per_stage["challenge"] += ex[p.kind]["k_challenge"] * p.n_equation_items
+            per_stage["equation"] += ex[p.kind]["k_equation"] * p.n_equation_items * NEQ[p.kind]
+        if dom in per_stage:
+            ex_dom = per_stage[dom] / (stage_ms[dom] * 1e-3) / 1e12
+            ex_step = sum(per_stage.values()) / (ms_dev / args.steps * 1e-3) / 1e12
+            executed = {"achieved": ex_dom, "frac": ex_dom / peak, "mac32_per_unit": {k: ex[shards[0][0].kind]["k_" + k] for k in per_stage},
+                        "step": {"achieved": ex_step, "frac": ex_step / peak, "mac32_per_step_per_gpu": sum(per_stage.values())},
+                        "source": os.path.relpath(ex_file, ROOT),
+                        "note": "executed 32x32->64 multiplies (IMAD.WIDE + IMAD.HI thread instructions counted by ncu per unit of each kernel) x the units "
+                                "of this step / measured time / peak: the integer-multiply pipe efficiency; rtest and finalize are left out (< 1 % of the step)"}
     except Exception:
         pass
     roofline = {"bound": "int32_mul", "kernel": {"decode": "k_decode", "challenge": "k_challenge", "aggregate": "k_aggregate", "equation": "k_equation"}[dom],
-                "achieved": achieved, "peak": peak, "unit": "TMAC32/s", "frac": achieved / peak, "traffic": traffic,
+                "achieved": achieved, "peak": peak, "unit": "TMAC32/s", "frac": achieved / peak, "executed": executed, "traffic": traffic,
                 "traffic_unit": "DRAM bytes per step (ncu dram__bytes_read.sum + dram__bytes_write.sum, the newest profiles/r*_ncu_traffic.json); secondary: the bound is the multiply pipe",
                 "peak_source": peak_src,
                 "ms_per_step": stage_ms[dom], "algorithmic_mac32_per_step": canon[dom],
                 "note": "achieved = canonical MAC32 (SURVEY 8(d) / Appendix C operation counts at 136/108 MAC32 per field mul/sqr) of the kernel's units / its measured time "
                         "(equation kernel: only the equations it evaluates -- items that fail to decode or have an invalid key never reach it); "
-                        "the implementation executes fewer multiplies than the canonical algorithm (Tate subgroup test, integer MDS, half-size scalars), so fractions above 1 are possible",
+                        "the implementation executes fewer multiplies than the canonical algorithm (Tate subgroup test, integer MDS, half-size scalars), so frac can exceed 1: "
+                        "`executed` is the efficiency figure",
                 "step": {"achieved": step_achieved, "frac": step_achieved / peak, "mac32_per_step_per_gpu": step_mac32},
                 "stage_ms_per_step": stage_ms,
                 "stage_timing": "per-stage CUDA events on the launching stream in a second pass of the same steps with the launches serialised "
                                 "(the timed pass overlaps neighbouring sub-chunks on two streams); ms_per_step of the kernel above is from that pass",
                 "hbm_secondary": {"algorithmic_GBps": (bytes_in + items_per_device * 33) / (ms_dev / args.steps * 1e-3) / 1e9, "measured_peak_GBps": hbm_peak}}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------
+    # ---- strong scaling of the library's own sharding: BASELINE.json configs[4] -------------------------------------------------
+    strong = None
+    if not args.no_strong:
+        gloo = dist.new_group(backend="gloo") if world > 1 else None     # the waiting ranks must not spin on their GPUs
+        barrier()
+        if rank == 0:
+            strong = strong_scaling_record(args, torch, wl, BatchVerifier, n_gpus_total if world > 1 else len(devices))
+        if gloo is not None:
+            dist.barrier(group=gloo)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): BASELINE.json configs[0] -----------------------------------------------------
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle as co
         co.build()
         threads = host_threads()
-        sample = int(args.cpu_sample or 1 << 13)
-        shards[0][0].cpu_check(co, 256, threads)
+        shards[0][0].cpu_check(co, 512, threads)      # the oracle agrees with the GPU on the head of the timed batch
+        n_cpu = int(args.cpu_sample or 1 << 16)
+        pk, sig, msg = co.gen_single(0xB200, n_cpu, threads=threads)
         t0 = time.perf_counter()
-        done = sum(p.cpu_check(co, max(1, sample * p.n // items_per_device), threads) for p in shards[0])
+        st, _ = co.verify_single(pk, sig, msg, threads=threads)
         dt = time.perf_counter() - t0
-        cpu = {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {done} items of the same batch(es), oracle/jjs_oracle.c (C restatement of the reference algorithm, {threads} threads); statuses equal the GPU's"}
+        assert not st.any()
+        cpu = {"value": n_cpu / dt, "unit": UNIT, "cores": threads, "kind": "port", "per_thread": n_cpu / dt / threads, "nproc": os.cpu_count(),
+               "sample": f"BASELINE.json configs[0]: {n_cpu} valid single signatures, PublicKey::verify restated in C (oracle/jjs_oracle.c), {threads} threads, one pass; "
+                         "the first 512 items of the GPU batch went through the same port and agree with the GPU"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "mixed5" else "weak", "vs_baseline": None,
                 "dtype": "u32 (8x32-bit Montgomery limbs, IMAD.WIDE)", "data": "synthetic", "config": workload_config(args),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "impl": "b200"}
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "host_memory": "pinned", "call": "one jjs_verify_mixed per step"},
+                "e2e_pageable": {"value": items_per_device * n_gpus_total * args.steps / pageable_s, "unit": UNIT, "ms_per_step": 1e3 * pageable_s / args.steps,
+                                 "host_memory": "pageable (numpy arrays, what a Rust Vec<u8> is)", "ratio_to_pinned": e2e_s / pageable_s},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "strong_2p24": strong, "cpu_baseline": cpu, "impl": "b200"}
         print(json.dumps(line), flush=True)
     bv.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling_record(args, torch, wl, BatchVerifier, n_devices):
+    """BASELINE.json configs[4]: 2^24 items, half single half double, 10 % invalid, through ONE context over n_devices GPUs.
+    e2e: one jjs_verify_mixed host call per step (pinned buffers; also pageable).  value: the same shards resident on the devices,
+    enqueued through the device entry points, CUDA events per device, max over devices."""
+    log2n = args.strong_log2n
+    half = 1 << (log2n - 1)
+    steps, warm = max(1, min(args.steps, 4)), 1
+    with BatchVerifier(list(range(n_devices))) as sv:
+        batches = [(wl.SINGLE,) + tuple(wl.make_batch(sv, wl.SINGLE, half, 0.10, seed=0x24A)[:4]), (wl.DOUBLE,) + tuple(wl.make_batch(sv, wl.DOUBLE, half, 0.10, seed=0x24B)[:4])]
+        n = 2 * half
+        pinned = [[torch.from_numpy(x).pin_memory() for x in b[1:4]] + [torch.empty(half, dtype=torch.uint8).pin_memory()] for b in batches]
+        pstat = [np.empty(half, dtype=np.uint8) for _ in batches]
+        t_pin = [(b[0], h[0].data_ptr(), None, h[1].data_ptr(), h[2].data_ptr(), half, h[3].data_ptr(), None, None, None) for b, h in zip(batches, pinned)]
+        t_page = [(b[0], b[1].ctypes.data, None, b[2].ctypes.data, b[3].ctypes.data, half, st.ctypes.data, None, None, None) for b, st in zip(batches, pstat)]
+
+        def sync_all():
+            for k in range(n_devices):
+                torch.cuda.synchronize(k)
+
+        def timed(tuples):
+            for _ in range(warm):
+                sv.verify_mixed_ptr(tuples)
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                sv.verify_mixed_ptr(tuples)
+            return (time.perf_counter() - t0) / steps
+
+        s_pin = timed(t_pin)
+        for b, h in zip(batches, pinned):
+            assert np.array_equal(h[3].numpy(), b[4]), "strong-scaling batch: statuses differ from the constructed expectation"
+        s_page = timed(t_page)
+        for b, st in zip(batches, pstat):
+            assert np.array_equal(st, b[4]), "strong-scaling batch (pageable): statuses differ from the constructed expectation"
+        # device-resident: contiguous shards of both kinds on every device
+        per = ((half + n_devices - 1) // n_devices + 31) & ~31
+        resident = []
+        for k in range(n_devices):
+            lo, hi = min(k * per, half), min(k * per + per, half)
+            dev = torch.device("cuda", k)
+            resident.append([(b[0], hi - lo, [torch.from_numpy(x[lo:hi]).to(dev) for x in b[1:4]], torch.empty(hi - lo, dtype=torch.uint8, device=dev), b[4][lo:hi])
+                             for b in batches])
+
+        def step_resident():
+            for k, parts in enumerate(resident):
+                stream = torch.cuda.current_stream(k).cuda_stream
+                for variant, m, d, st, _ in parts:
+                    if m:
+                        sv.verify_device(variant, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), m, st.data_ptr(), None, stream=stream, device_index=k)
+
+        for _ in range(warm):
+            step_resident()
+        sync_all()
+        events = []
+        for k in range(n_devices):
+            with torch.cuda.device(k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(torch.cuda.current_stream(k))
+                events.append((e0, e1))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_resident()
+        for k, (e0, e1) in enumerate(events):
+            with torch.cuda.device(k):
+                e1.record(torch.cuda.current_stream(k))
+        sync_all()
+        wall = (time.perf_counter() - t0) / steps
+        ms_dev = max(e0.elapsed_time(e1) for e0, e1 in events) / steps
+        for parts in resident:
+            for _, m, _, st, exp in parts:
+                assert np.array_equal(st.cpu().numpy(), exp), "strong-scaling batch (device-resident): statuses differ from the constructed expectation"
+    return {"workload": f"2^{log2n} items, half single half double, 10% invalid (BASELINE.json configs[4]); one jjs_ctx over {n_devices} device(s), contiguous shards, no collective",
+            "n_devices": n_devices, "items": n, "steps": steps, "warmup": warm,
+            "value": n / (ms_dev * 1e-3), "ms_per_step": ms_dev, "value_wall_clock": n / wall,
+            "e2e": {"value": n / s_pin, "ms_per_step": 1e3 * s_pin, "host_memory": "pinned", "call": "one jjs_verify_mixed",
+                    "h2d_bytes_per_step": sum(sum(x.nbytes for x in b[1:4]) for b in batches), "d2h_bytes_per_step": n},
+            "e2e_pageable": {"value": n / s_page, "ms_per_step": 1e3 * s_page, "ratio_to_pinned": s_pin / s_page},
+            "unit": UNIT, "scaling": "strong"}
 
 
 if __name__ == "__main__":

@@ -54,7 +54,9 @@ extern "C" {
 typedef struct jjs_ctx jjs_ctx;
 
 /* Create a context over the given CUDA device ordinals (n_devices >= 1; devices == NULL means device 0
- * .. n_devices-1).  Builds the per-device constant tables and allocates no batch memory yet. */
+ * .. n_devices-1).  Builds the per-device constant tables and allocates no batch memory yet.
+ * On failure *out still receives a context, for jjs_last_error only: every other entry point returns JJS_ERR_CUDA on
+ * it (there is no CPU fallback) and jjs_destroy frees it. */
 int jjs_init(const int* devices, int n_devices, jjs_ctx** out);
 void jjs_destroy(jjs_ctx* ctx);
 /* Human-readable description of the last failure on this context ("" if none). */
@@ -62,7 +64,10 @@ const char* jjs_last_error(const jjs_ctx* ctx);
 int jjs_device_count(const jjs_ctx* ctx);
 
 /* ---- host-buffer entry points: shard the batch contiguously over the context's devices, copy in,
- *      verify, copy the status bytes (and challenges) back.  All pointers are host memory. -------------- */
+ *      verify, copy the status bytes (and challenges) back.  All pointers are host memory (pinned or pageable: every
+ *      device of the context is driven by its own host thread for the duration of the call, so staged copies from
+ *      pageable memory on one device do not hold up the others).  The calls return when everything is done; if a call
+ *      fails, the devices are drained first, so nothing still reads or writes the caller's buffers. -------------- */
 
 /* PublicKey::verify for n (key, signature, message) triples.  reference src/keys/public.rs:114-135 */
 int jjs_verify_single(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n,
@@ -73,6 +78,13 @@ int jjs_verify_single(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, c
  * unused high bits of the last word are 0.  The bits are packed on the GPU with one warp ballot per word. */
 int jjs_verify_batch(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n,
                      uint32_t* accept_bitmap);
+/* The same packed accept bitmap for the other three kinds. */
+int jjs_verify_batch_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n,
+                            uint32_t* accept_bitmap);
+int jjs_verify_batch_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig64, const uint8_t* msg32, size_t n,
+                            uint32_t* accept_bitmap);
+int jjs_verify_batch_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* offsets, const uint8_t* sig64,
+                               const uint8_t* msg32, size_t n, uint32_t* accept_bitmap);
 /* PublicKeyDouble::verify.  reference src/keys/public/double.rs:86-117 */
 int jjs_verify_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n,
                       uint8_t* status, uint8_t* c32_or_null);
@@ -81,10 +93,35 @@ int jjs_verify_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig64, c
                       uint8_t* status, uint8_t* c32_or_null);
 /* multisig::aggregate_pk(&pks[offsets[i]..offsets[i+1]]).verify(sig_i, msg_i).
  * reference src/multisig.rs:154-156, 393-429 then src/keys/public.rs:114-135.
- * offsets has n + 1 entries; aggpk32_or_null receives PublicKey::to_bytes() of each aggregate key. */
+ * offsets has n + 1 entries; aggpk32_or_null receives PublicKey::to_bytes() of each aggregate key.  Any number of signers
+ * per item, as in the reference (the sponge tag of a 2 + 2 n element transcript is computed at call time); an item without
+ * signers aggregates to the identity and is reported JJS_INVALID_POINT, which is what verify() returns for that key. */
 int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* offsets, const uint8_t* sig64,
                          const uint8_t* msg32, size_t n, uint8_t* status, uint8_t* c32_or_null,
                          uint8_t* aggpk32_or_null);
+
+/* Several batches of different kinds in ONE call (BASELINE.json configs[3] and [4]: var-generator + aggregate-key items,
+ * single + double items).  Every part is split evenly over the context's devices (parts below 8 192 items per device go
+ * whole to the least loaded device, weighted by the cost of their kind), so each device carries the same share of every
+ * kind and all devices finish together; nothing is synchronised between the parts.  Per part, any of status / c32 /
+ * aggpk32 / accept_bitmap may be NULL, but status and accept_bitmap not both. */
+#define JJS_KIND_SINGLE 0
+#define JJS_KIND_DOUBLE 1
+#define JJS_KIND_VARGEN 2
+#define JJS_KIND_AGGREGATE 3
+typedef struct jjs_part {
+    int kind;                 /* JJS_KIND_* */
+    const uint8_t* pk;        /* kind 0: pk32;  1, 2: pk64;  3: pks32 (ragged, see offsets) */
+    const uint32_t* offsets;  /* kind 3: n + 1 entries;  NULL otherwise */
+    const uint8_t* sig;       /* kind 1: sig96;  otherwise sig64 */
+    const uint8_t* msg32;
+    size_t n;
+    uint8_t* status;          /* n status bytes */
+    uint8_t* c32;             /* n challenges (32 bytes each) */
+    uint8_t* aggpk32;         /* kind 3: n aggregate keys */
+    uint32_t* accept_bitmap;  /* (n + 31) / 32 words, as jjs_verify_batch */
+} jjs_part;
+int jjs_verify_mixed(jjs_ctx* ctx, const jjs_part* parts, size_t n_parts);
 
 /* ---- device-buffer entry points: inputs and outputs already live on device `device_index` of the context
  *      (an index into the list given to jjs_init); the work is ordered after everything `cuda_stream` holds at
@@ -108,7 +145,10 @@ int jjs_status_bitmap_device(jjs_ctx* ctx, int device_index, const uint8_t* d_st
                              void* cuda_stream);
 
 /* Aggregate-key verification on device buffers.  d_offsets / h_offsets: the same n + 1 offsets on the device and on
- * the host (the host copy plans the 2^20-item chunks). */
+ * the host (the host copy plans the chunks and is only read during the call).  Enqueue-only like the other *_device
+ * calls: the ordering of a chunk by signer count happens on the device.  The one exception is growth of the library's
+ * key scratch or tag table (the first aggregate call on a device, more than 2^21 signer keys in one 2^18-item chunk, or
+ * more than 511 signers in one item), which waits for the device once. */
 int jjs_verify_aggregate_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pks32, const uint32_t* d_offsets,
                                 const uint32_t* h_offsets, const uint8_t* d_sig64, const uint8_t* d_msg32, size_t n,
                                 uint8_t* d_status, uint8_t* d_c32_or_null, uint8_t* d_aggpk32_or_null, void* cuda_stream);
@@ -131,7 +171,7 @@ int jjs_points_to_ext(jjs_ctx* ctx, const uint8_t* points32, const uint8_t* z_mo
 /* multisig::combine for n sessions (reference src/multisig.rs:311-347; the share check is verify_share,
  * src/multisig.rs:255-281, 366-387).  Session i owns participants offsets[i] .. offsets[i+1]-1 of the ragged arrays
  * pks32 (PublicKey::to_bytes), R32 / S32 (compressed commitment points) and z32 (JubJubScalar::to_bytes shares);
- * msg32 has one BlsScalar per session; at most 31 participants per session.  Per session:
+ * msg32 has one BlsScalar per session; any number of participants per session.  Per session:
  *   status 0: Ok(Signature), sig64 = (sum z_i) || RSa       5: Err(InvalidMultisigShare(bad_index))
  *          3: some field fails from_bytes                     4: Err(InvalidMultisigTranscript) (no participants)
  * share_ok (one byte per participant) is what verify_share returns for every participant, not only the first bad

@@ -16,8 +16,16 @@ EXPORTS = [
     "jjs_verify_single", "jjs_verify_double", "jjs_verify_vargen", "jjs_verify_aggregate",
     "jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device",
     "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect", "jjs_subgroup_check", "jjs_verify_aggregate_device", "jjs_sign_aggregate_batch", "jjs_verify_ext", "jjs_points_to_ext", "jjs_multisig_combine",
-    "jjs_verify_batch", "jjs_status_bitmap_device",
+    "jjs_verify_batch", "jjs_status_bitmap_device", "jjs_verify_batch_double", "jjs_verify_batch_vargen", "jjs_verify_batch_aggregate",
+    "jjs_verify_mixed",
 ]
+
+
+class Part(C.Structure):
+    """struct jjs_part of include/jjschnorr_b200.h"""
+    _fields_ = [("kind", C.c_int), ("pk", C.c_void_p), ("offsets", C.c_void_p), ("sig", C.c_void_p), ("msg32", C.c_void_p), ("n", C.c_size_t),
+                ("status", C.c_void_p), ("c32", C.c_void_p), ("aggpk32", C.c_void_p), ("accept_bitmap", C.c_void_p)]
+
 
 _lib = None
 
@@ -52,6 +60,14 @@ def lib():
         f.restype = C.c_int
     L.jjs_verify_batch.argtypes = [vp, vp, vp, vp, sz, vp]
     L.jjs_verify_batch.restype = C.c_int
+    for name in ("jjs_verify_batch_double", "jjs_verify_batch_vargen"):
+        f = getattr(L, name)
+        f.argtypes = [vp, vp, vp, vp, sz, vp]
+        f.restype = C.c_int
+    L.jjs_verify_batch_aggregate.argtypes = [vp, vp, vp, vp, vp, sz, vp]
+    L.jjs_verify_batch_aggregate.restype = C.c_int
+    L.jjs_verify_mixed.argtypes = [vp, C.POINTER(Part), sz]
+    L.jjs_verify_mixed.restype = C.c_int
     L.jjs_status_bitmap_device.argtypes = [vp, C.c_int, vp, sz, vp, vp]
     L.jjs_status_bitmap_device.restype = C.c_int
     L.jjs_verify_aggregate.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp]

@@ -8,9 +8,9 @@ import numpy as np
 from . import _native
 
 STATUS_OK, STATUS_INVALID_SIGNATURE, STATUS_INVALID_POINT, STATUS_BYTES_ERROR = 0, 1, 2, 3
-SINGLE, DOUBLE, VARGEN = 0, 1, 2
-PK_SIZE = {SINGLE: 32, DOUBLE: 64, VARGEN: 64}
-SIG_SIZE = {SINGLE: 64, DOUBLE: 96, VARGEN: 64}
+SINGLE, DOUBLE, VARGEN, AGGREGATE = 0, 1, 2, 3
+PK_SIZE = {SINGLE: 32, DOUBLE: 64, VARGEN: 64, AGGREGATE: 32}
+SIG_SIZE = {SINGLE: 64, DOUBLE: 96, VARGEN: 64, AGGREGATE: 64}
 
 
 class JjsError(RuntimeError):
@@ -104,6 +104,72 @@ class BatchVerifier:
         words = np.zeros((n + 31) // 32, dtype=np.uint32)
         self._check(self._lib.jjs_verify_batch(self._ctx, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, n, words.ctypes.data), "jjs_verify_batch")
         return words
+
+    def _verify_bitmap(self, variant, fn, name, pk, sig, msg):
+        pk, sig, msg = _u8(pk, PK_SIZE[variant], "pk"), _u8(sig, SIG_SIZE[variant], "sig"), _u8(msg, 32, "msg")
+        n = msg.shape[0]
+        if pk.shape[0] != n or sig.shape[0] != n:
+            raise ValueError("pk, sig and msg must describe the same number of items")
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(fn(self._ctx, pk.ctypes.data, sig.ctypes.data, msg.ctypes.data, n, words.ctypes.data), name)
+        return words
+
+    def verify_batch_double(self, pk64, sig96, msg32):
+        return self._verify_bitmap(DOUBLE, self._lib.jjs_verify_batch_double, "jjs_verify_batch_double", pk64, sig96, msg32)
+
+    def verify_batch_vargen(self, pk64, sig64, msg32):
+        return self._verify_bitmap(VARGEN, self._lib.jjs_verify_batch_vargen, "jjs_verify_batch_vargen", pk64, sig64, msg32)
+
+    def verify_batch_aggregate(self, pks32, offsets, sig64, msg32):
+        pks, sig, msg = _u8(pks32, 32, "pks"), _u8(sig64, 64, "sig"), _u8(msg32, 32, "msg")
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = msg.shape[0]
+        if offsets.shape[0] != n + 1 or sig.shape[0] != n or int(offsets[-1]) != pks.shape[0] or int(offsets[0]) != 0:
+            raise ValueError("offsets must have n + 1 entries covering pks32 exactly")
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(self._lib.jjs_verify_batch_aggregate(self._ctx, pks.ctypes.data, offsets.ctypes.data, sig.ctypes.data, msg.ctypes.data, n,
+                                                         words.ctypes.data), "jjs_verify_batch_aggregate")
+        return words
+
+    def verify_mixed(self, parts, want_challenge=False, want_bitmap=False):
+        """Several batches of different kinds in one call (jjs_verify_mixed).  parts: iterable of (kind, pk, sig, msg) or, for
+        AGGREGATE, (kind, pks, sig, msg, offsets).  Returns one dict per part: status, and c / aggpk / bitmap when asked for."""
+        structs, keep, out = [], [], []
+        for part in parts:
+            kind, pk, sig, msg = part[0], part[1], part[2], part[3]
+            pk, sig, msg = _u8(pk, PK_SIZE[kind], "pk"), _u8(sig, SIG_SIZE[kind], "sig"), _u8(msg, 32, "msg")
+            n = msg.shape[0]
+            off = None
+            if kind == AGGREGATE:
+                off = np.ascontiguousarray(part[4], dtype=np.uint32)
+                if off.shape[0] != n + 1 or int(off[-1]) != pk.shape[0] or int(off[0]) != 0:
+                    raise ValueError("offsets must have n + 1 entries covering pks32 exactly")
+            elif pk.shape[0] != n:
+                raise ValueError("pk, sig and msg must describe the same number of items")
+            if sig.shape[0] != n:
+                raise ValueError("pk, sig and msg must describe the same number of items")
+            res = {"status": np.empty(n, dtype=np.uint8)}
+            if want_challenge:
+                res["c"] = np.empty((n, 32), dtype=np.uint8)
+            if kind == AGGREGATE:
+                res["aggpk"] = np.empty((n, 32), dtype=np.uint8)
+            if want_bitmap:
+                res["bitmap"] = np.zeros((n + 31) // 32, dtype=np.uint32)
+            ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+            structs.append(_native.Part(kind, ptr(pk), ptr(off), ptr(sig), ptr(msg), n, ptr(res["status"]), ptr(res.get("c")), ptr(res.get("aggpk")),
+                                        ptr(res.get("bitmap"))))
+            keep.append((pk, sig, msg, off))
+            out.append(res)
+        arr = (_native.Part * len(structs))(*structs)
+        self._check(self._lib.jjs_verify_mixed(self._ctx, arr, len(structs)), "jjs_verify_mixed")
+        return out
+
+    def verify_mixed_ptr(self, parts):
+        """jjs_verify_mixed on raw host pointers (e.g. pinned torch tensors): parts = iterable of
+        (kind, pk_ptr, offsets_ptr_or_None, sig_ptr, msg_ptr, n, status_ptr, c_ptr_or_None, aggpk_ptr_or_None, bitmap_ptr_or_None)."""
+        structs = [_native.Part(*p) for p in parts]
+        arr = (_native.Part * len(structs))(*structs)
+        self._check(self._lib.jjs_verify_mixed(self._ctx, arr, len(structs)), "jjs_verify_mixed")
 
     @staticmethod
     def unpack_bitmap(words, n):

@@ -35,6 +35,7 @@ struct Tables {
     const uint8_t* dlog_hash;  // [1 << JJS_DLOG_HASH_BITS]
     const niels* fb_g;         // [FB_WINDOWS][FB_ENTRIES]  j * 2^(FB_W w) * G
     const niels* fb_gn;        // same for G' (GENERATOR_NUMS_EXTENDED)
+    const fq* safe_tags;       // [n]  SAFE sponge tag for n absorbed elements (host-computed, safe_tag.h); multisig transcripts only
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -454,7 +455,8 @@ JJS_HD void varbase_mul(ext& r, const fq* tab, size_t stride, const DIGITS& digi
 }
 
 // acc = sum_i 16^i (dA[i] * A + dB[i] * B) over N signed radix-16 digits each (Straus: the doublings are shared);
-// tabA / tabB are per-thread tables from varbase_table_build.  acc.T is defined on return.
+// tabA / tabB are per-thread tables from varbase_table_build.  acc.T is defined on return.  The second addition of a
+// window is followed by a doubling, which does not read T, so it skips that product in every window but the last.
 template <int N>
 JJS_HD void straus2(ext& r, const fq* tabA, const fq* tabB, size_t stride, const int8_t* dA, const int8_t* dB) {
     ext acc, t;
@@ -474,7 +476,8 @@ JJS_HD void straus2(ext& r, const fq* tabA, const fq* tabB, size_t stride, const
         ext_add_pniels<true>(t, acc, n);
         pniels_load(n, tabB, stride, db < 0 ? -db : db);
         pniels_cneg(n, db < 0);
-        ext_add_pniels<true>(acc, t, n);
+        if (i != 0) ext_add_pniels<false>(acc, t, n);
+        else ext_add_pniels<true>(acc, t, n);
     }
     r = acc;
 }
@@ -521,6 +524,22 @@ JJS_HD void fixedbase_mul(ext& r, const niels* table, const uint32_t* k) {
         acc = t;
     }
     r = acc;
+}
+
+// acc += k * B (acc.T defined on entry; not on return): the windows are added straight onto a running sum, which saves the
+// separate accumulator of fixedbase_mul and the conversion and addition that would join the two
+JJS_HD void fixedbase_acc(ext& acc, const niels* table, const uint32_t* k) {
+#pragma unroll 1
+    for (int w = 0; w < FB_WINDOWS; w++) {
+        int bit = w * FB_W;
+        uint32_t lo = k[bit >> 5] >> (bit & 31);
+        if ((bit & 31) + FB_W > 32 && (bit >> 5) + 1 < 8) lo |= k[(bit >> 5) + 1] << (32 - (bit & 31));
+        uint32_t idx = lo & (FB_ENTRIES - 1);
+        niels n = table[(size_t)w * FB_ENTRIES + idx];
+        ext t;
+        ext_add_niels<true>(t, acc, n);
+        acc = t;
+    }
 }
 
 // One entry of a fixed-base window table: j * 2^(FB_W w) * B as affine Niels (table construction only).

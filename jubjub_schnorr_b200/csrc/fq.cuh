@@ -27,6 +27,11 @@ struct uint4 {  // host twin of the CUDA vector type (tests/hostsim only)
 
 namespace jjs {
 
+#if !defined(__CUDA_ARCH__)
+// host twin only: a carry the device code drops as provably zero was not zero (tests/hostsim aborts loudly)
+[[noreturn]] inline void jjs_host_bound_violation() { __builtin_trap(); }
+#endif
+
 // q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, little-endian 32-bit limbs.
 // -q^-1 mod 2^32 = 0xffffffff, so the Montgomery quotient digit is just the negated low limb.
 #define JJS_Q_LIMBS {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u}
@@ -44,17 +49,53 @@ JJS_HD uint32_t q_limb(int i) {
 // carry-chain building blocks (device: one asm block each; host: exact C++ twin)
 // ---------------------------------------------------------------------------------------------
 
-// acc[0..2N) += a[k] * b with product k at limb pair (2k, 2k+1); acc[2N] += carry out.  N in 1..4.
-template <int N>
+// acc[0..2N) += a[k] * b with product k at limb pair (2k, 2k+1).  N in 1..4.  The carry out of limb 2N - 1 is
+//   CAP == 2: added to acc[2N];   CAP == 1: stored to acc[2N] (the caller knows that limb is still untouched);
+//   CAP == 0: dropped (the caller knows it is zero, see mul_wide / sqr_wide).
+// ptxas turns every captured carry into a SEL plus, when it is accumulated, an IMAD.X and often an IMAD.MOV that zeroes
+// the upper half of the 64-bit accumulator pair -- instructions on the multiply pipe -- so captures are only taken
+// where a carry can exist.
+template <int N, int CAP = 2>
 JJS_HD void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
-    if (N == 1) {
+    if (N == 1 && CAP == 0) {
+        asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+            "madc.hi.u32 %1, %2, %3, %1;"
+            : "+r"(acc[0]), "+r"(acc[1])
+            : "r"(a[0]), "r"(b));
+    }
+    else if (N == 1 && CAP == 1) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "=r"(acc[2])
+            : "r"(a[0]), "r"(b));
+    }
+    else if (N == 1 && CAP == 2) {
         asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
             "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
             "addc.u32 %2, %2, 0;"
             : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
             : "r"(a[0]), "r"(b));
-    } else if (N == 2) {
+    }
+    else if (N == 2 && CAP == 0) {
+        asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t"
+            "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+            "madc.lo.cc.u32 %2, %5, %6, %2;\n\t"
+            "madc.hi.u32 %3, %5, %6, %3;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3])
+            : "r"(a[0]), "r"(a[1]), "r"(b));
+    }
+    else if (N == 2 && CAP == 1) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(acc[4])
+            : "r"(a[0]), "r"(a[1]), "r"(b));
+    }
+    else if (N == 2 && CAP == 2) {
         asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
             "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
             "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
@@ -62,7 +103,29 @@ JJS_HD void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
             "addc.u32 %4, %4, 0;"
             : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
             : "r"(a[0]), "r"(a[1]), "r"(b));
-    } else if (N == 3) {
+    }
+    else if (N == 3 && CAP == 0) {
+        asm("mad.lo.cc.u32 %0, %6, %9, %0;\n\t"
+            "madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+            "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+            "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+            "madc.lo.cc.u32 %4, %8, %9, %4;\n\t"
+            "madc.hi.u32 %5, %8, %9, %5;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b));
+    }
+    else if (N == 3 && CAP == 1) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(acc[6])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b));
+    }
+    else if (N == 3 && CAP == 2) {
         asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
             "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
             "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
@@ -72,7 +135,33 @@ JJS_HD void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
             "addc.u32 %6, %6, 0;"
             : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b));
-    } else {
+    }
+    else if (N == 4 && CAP == 0) {
+        asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+            "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+            "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+            "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+            "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+            "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+            "madc.hi.u32 %7, %11, %12, %7;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b));
+    }
+    else if (N == 4 && CAP == 1) {
+        asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(acc[8])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b));
+    }
+    else if (N == 4 && CAP == 2) {
         asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
             "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
             "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
@@ -82,8 +171,7 @@ JJS_HD void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
             "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
             "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
             "addc.u32 %8, %8, 0;"
-            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
-              "+r"(acc[7]), "+r"(acc[8])
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b));
     }
 #else
@@ -96,7 +184,9 @@ JJS_HD void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
         acc[2 * k + 1] = (uint32_t)hi;
         c = hi >> 32;
     }
-    acc[2 * N] += (uint32_t)c;
+    if (CAP == 2) acc[2 * N] += (uint32_t)c;
+    else if (CAP == 1) { if (acc[2 * N] != 0) jjs_host_bound_violation(); acc[2 * N] = (uint32_t)c; }
+    else if (c != 0) jjs_host_bound_violation();   // the twin checks the bounds the device code relies on
 #endif
 }
 
@@ -342,6 +432,78 @@ JJS_HD void redc_step(const uint32_t* ev, uint32_t* od, uint32_t* n, uint32_t in
 #endif
 }
 
+
+// ---- additive reduction on the complement of q --------------------------------------------------------------------
+// q == 1 (mod 2^32) makes the Montgomery quotient digit of a value with low limb e0 equal to -e0.  Instead of negating
+// it (and patching the multiplier-free products of q's two low limbs with m - [m != 0]) the step below adds
+//     e0 * qbar,  qbar = 2^256 - q = (0xffffffff, 0, 0x0001a401, 0xac425bfd, 0xf65e27fa, 0xccc627f7, 0xd66282b7, 0x8c1258ac),
+// which cancels the low limb just the same (e0 + e0 * 0xffffffff = e0 * 2^32, exactly: limb 1 receives e0 and nothing
+// else, qbar's limb 1 being zero) but is e0 * 2^256 too much.  Over the eight steps the excess adds up to M * 2^256 with
+// M = sum e0_k 2^(32 k), i.e. the reduced value comes out as r + M, and one 8-limb subtraction at the end removes it:
+//     r = (T + M qbar) / 2^256 - M = (T - M q) / 2^256  in (-q, q)  for T < q 2^256;  a borrow means "add q".
+// Same six wide multiplies per step; the negation, the min and the extra subtraction of every step are gone (they
+// compiled to IMAD.MOV / VIMNMX / IMAD.IADD, two of the three on the multiply pipe).
+JJS_HD void redc_step2(const uint32_t* ev, uint32_t* od, uint32_t* n, uint32_t inject, uint32_t& e0_out) {
+#if defined(__CUDA_ARCH__)
+    uint32_t e0;
+    asm("add.cc.u32 %9, %10, %11;\n\t"           // e0 = od0 + ev1, CF feeds limb 1
+        "addc.cc.u32 %0, %12, %9;\n\t"           // n0 = ev2 + e0 + CF
+        "addc.cc.u32 %1, %13, 0;\n\t"            // n1 = ev3 + CF
+        "madc.lo.cc.u32 %2, %9, 0xac425bfd, %14;\n\t"
+        "madc.hi.cc.u32 %3, %9, 0xac425bfd, %15;\n\t"
+        "madc.lo.cc.u32 %4, %9, 0xccc627f7, %16;\n\t"
+        "madc.hi.cc.u32 %5, %9, 0xccc627f7, %17;\n\t"
+        "madc.lo.cc.u32 %6, %9, 0x8c1258ac, %18;\n\t"
+        "madc.hi.cc.u32 %7, %9, 0x8c1258ac, %19;\n\t"
+        "addc.u32 %8, 0, 0;"                       // the running value stays below 2^256 + qbar: this limb is 0 or 1
+        : "=&r"(n[0]), "=&r"(n[1]), "=&r"(n[2]), "=&r"(n[3]), "=&r"(n[4]), "=&r"(n[5]), "=&r"(n[6]), "=&r"(n[7]), "=&r"(n[8]), "=&r"(e0)
+        : "r"(od[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(inject));
+    asm("mad.lo.cc.u32 %0, %7, 0x0001a401, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, 0x0001a401, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, 0xf65e27fa, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, 0xf65e27fa, %3;\n\t"
+        "madc.lo.cc.u32 %4, %7, 0xd66282b7, %4;\n\t"
+        "madc.hi.cc.u32 %5, %7, 0xd66282b7, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8])
+        : "r"(e0));
+    od[0] = 0;
+    e0_out = e0;
+#else
+    constexpr uint32_t QB[8] = {0xffffffffu, 0u, 0x0001a401u, 0xac425bfdu, 0xf65e27fau, 0xccc627f7u, 0xd66282b7u, 0x8c1258acu};
+    uint64_t s = (uint64_t)od[0] + ev[1];
+    uint32_t e0 = (uint32_t)s;
+    uint64_t c = s >> 32;
+    uint64_t t = (uint64_t)ev[2] + e0 + c;
+    n[0] = (uint32_t)t;
+    t = (uint64_t)ev[3] + (t >> 32);
+    n[1] = (uint32_t)t;
+    c = t >> 32;
+    const uint32_t addend[6] = {ev[4], ev[5], ev[6], ev[7], ev[8], inject};
+    for (int k = 0; k < 3; k++) {
+        uint64_t p = (uint64_t)e0 * QB[2 * k + 3];
+        uint64_t lo = (uint64_t)addend[2 * k] + (uint32_t)p + c;
+        n[2 * k + 2] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)addend[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+        n[2 * k + 3] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    n[8] = (uint32_t)c;
+    c = 0;
+    for (int k = 0; k < 3; k++) {
+        uint64_t p = (uint64_t)e0 * QB[2 * k + 2];
+        uint64_t lo = (uint64_t)od[2 * k + 2] + (uint32_t)p + c;
+        od[2 * k + 2] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)od[2 * k + 3] + (uint32_t)(p >> 32) + (lo >> 32);
+        od[2 * k + 3] = (uint32_t)hi;
+        c = hi >> 32;
+    }
+    od[8] += (uint32_t)c;
+    od[0] = 0;
+    e0_out = e0;
+#endif
+}
+
 JJS_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi) {  // (hi:lo << 1) >> 32
 #if defined(__CUDA_ARCH__)
     return __funnelshift_l(lo, hi, 1);
@@ -362,12 +524,20 @@ JJS_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
     for (int i = 0; i < 15; i++) O[i] = 0;
     const uint32_t ae[4] = {a[0], a[2], a[4], a[6]}, ao[4] = {a[1], a[3], a[5], a[7]};
+    // Carry out of a row: all products accumulated so far lie on diagonals <= p + 6 for a row at offset p, so limbs
+    // [p, p + 8) can only overflow when TWO products sit on diagonal p + 6, i.e. for the second row at an offset (the
+    // lower diagonals add < 2^195 to a first product < 2^256 - 2^225).  The first row at an offset therefore drops its
+    // carry, the second stores it into the limb above, which no earlier row has touched.
+    mad_row<4, 0>(E + 0, ae, b[0]);
+    mad_row<4, 0>(O + 0, ao, b[0]);
+    mad_row<4, 1>(O + 0, ae, b[1]);
+    mad_row<4, 0>(E + 2, ao, b[1]);
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        mad_row<4>(E + i, ae, b[i]);
-        mad_row<4>(O + i, ao, b[i]);
-        mad_row<4>(O + i, ae, b[i + 1]);
-        mad_row<4>(E + i + 2, ao, b[i + 1]);
+    for (int i = 2; i < 8; i += 2) {
+        mad_row<4, 1>(E + i, ae, b[i]);
+        mad_row<4, 0>(O + i, ao, b[i]);
+        mad_row<4, 1>(O + i, ae, b[i + 1]);
+        mad_row<4, 0>(E + i + 2, ao, b[i + 1]);
     }
     // t = E + (O << 32)
     t[0] = E[0];
@@ -385,20 +555,22 @@ JJS_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
     uint32_t E[16], O[16];  // E[k]: limb k;  O[k]: limb k+1
 #pragma unroll
     for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
-    // row i multiplies a[i] with a[j], j > i: j - i odd -> odd accumulator, j - i even -> even accumulator
-    { const uint32_t m[4] = {a[1], a[3], a[5], a[7]}; mad_row<4>(O + 0, m, a[0]); }    // limbs 1..8
-    { const uint32_t m[3] = {a[2], a[4], a[6]};       mad_row<3>(E + 2, m, a[0]); }    // limbs 2..7
-    { const uint32_t m[3] = {a[2], a[4], a[6]};       mad_row<3>(O + 2, m, a[1]); }    // limbs 3..8
-    { const uint32_t m[3] = {a[3], a[5], a[7]};       mad_row<3>(E + 4, m, a[1]); }    // limbs 4..9
-    { const uint32_t m[3] = {a[3], a[5], a[7]};       mad_row<3>(O + 4, m, a[2]); }    // limbs 5..10
-    { const uint32_t m[2] = {a[4], a[6]};             mad_row<2>(E + 6, m, a[2]); }    // limbs 6..9
-    { const uint32_t m[2] = {a[4], a[6]};             mad_row<2>(O + 6, m, a[3]); }    // limbs 7..10
-    { const uint32_t m[2] = {a[5], a[7]};             mad_row<2>(E + 8, m, a[3]); }    // limbs 8..11
-    { const uint32_t m[2] = {a[5], a[7]};             mad_row<2>(O + 8, m, a[4]); }    // limbs 9..12
-    { const uint32_t m[1] = {a[6]};                   mad_row<1>(E + 10, m, a[4]); }   // limbs 10..11
-    { const uint32_t m[1] = {a[6]};                   mad_row<1>(O + 10, m, a[5]); }   // limbs 11..12
-    { const uint32_t m[1] = {a[7]};                   mad_row<1>(E + 12, m, a[5]); }   // limbs 12..13
-    { const uint32_t m[1] = {a[7]};                   mad_row<1>(O + 12, m, a[6]); }   // limbs 13..14
+    // row i multiplies a[i] with a[j], j > i: j - i odd -> odd accumulator, j - i even -> even accumulator.
+    // Carries out of a row (see mul_wide): only possible when the row's top product is the second one on its diagonal
+    // in that accumulator; it is then stored into the limb above, which is still untouched.
+    { const uint32_t m[4] = {a[1], a[3], a[5], a[7]}; mad_row<4, 0>(O + 0, m, a[0]); }    // limbs 1..8,   top a0 a7: first on diagonal 7
+    { const uint32_t m[3] = {a[2], a[4], a[6]};       mad_row<3, 0>(E + 2, m, a[0]); }    // limbs 2..7,   top a0 a6: first on 6
+    { const uint32_t m[3] = {a[2], a[4], a[6]};       mad_row<3, 1>(O + 2, m, a[1]); }    // limbs 3..8,   top a1 a6: second on 7 -> O[8]
+    { const uint32_t m[3] = {a[3], a[5], a[7]};       mad_row<3, 0>(E + 4, m, a[1]); }    // limbs 4..9,   top a1 a7: first on 8
+    { const uint32_t m[3] = {a[3], a[5], a[7]};       mad_row<3, 0>(O + 4, m, a[2]); }    // limbs 5..10,  top a2 a7: first on 9
+    { const uint32_t m[2] = {a[4], a[6]};             mad_row<2, 1>(E + 6, m, a[2]); }    // limbs 6..9,   top a2 a6: second on 8 -> E[10]
+    { const uint32_t m[2] = {a[4], a[6]};             mad_row<2, 1>(O + 6, m, a[3]); }    // limbs 7..10,  top a3 a6: second on 9 -> O[10]
+    { const uint32_t m[2] = {a[5], a[7]};             mad_row<2, 0>(E + 8, m, a[3]); }    // limbs 8..11,  top a3 a7: first on 10
+    { const uint32_t m[2] = {a[5], a[7]};             mad_row<2, 0>(O + 8, m, a[4]); }    // limbs 9..12,  top a4 a7: first on 11
+    { const uint32_t m[1] = {a[6]};                   mad_row<1, 1>(E + 10, m, a[4]); }   // limbs 10..11, top a4 a6: second on 10 -> E[12]
+    { const uint32_t m[1] = {a[6]};                   mad_row<1, 1>(O + 10, m, a[5]); }   // limbs 11..12, top a5 a6: second on 11 -> O[12]
+    { const uint32_t m[1] = {a[7]};                   mad_row<1, 0>(E + 12, m, a[5]); }   // limbs 12..13, top a5 a7: first on 12
+    { const uint32_t m[1] = {a[7]};                   mad_row<1, 0>(O + 12, m, a[6]); }   // limbs 13..14, top a6 a7: first on 13
     // s = E + (O << 32): limbs 1..15
     uint32_t s[16];
     s[0] = 0;
@@ -417,7 +589,10 @@ JJS_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
     mad_diag8(t, a);
 }
 
-// r = t / 2^256 mod q for a 16-limb t < q * 2^256 (so the result is < 2q before the final subtraction).
+#ifndef JJS_REDC2
+#define JJS_REDC2 1
+#endif
+// r = t / 2^256 mod q for a 16-limb t < q * 2^256, fully reduced.
 JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     uint32_t ev[9], od[9], n[9];
     ev[0] = 0;
@@ -425,6 +600,20 @@ JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     for (int i = 0; i < 8; i++) ev[i + 1] = t[i];
 #pragma unroll
     for (int i = 0; i < 9; i++) od[i] = 0;
+#if JJS_REDC2
+    uint32_t M[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        redc_step2(ev, od, n, t[8 + i], M[i]);
+#pragma unroll
+        for (int k = 0; k < 9; k++) { ev[k] = od[k]; od[k] = n[k]; }
+    }
+    // r + M = (ev >> 32) + od < 2^256;  r = that - M, plus q if it went negative
+    uint32_t v[8], d[8];
+    add8(v, ev + 1, od);
+    uint32_t borrow = sub8(d, v, M);
+    add_q_masked(r, d, borrow);
+#else
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         redc_step(ev, od, n, t[8 + i]);
@@ -438,6 +627,7 @@ JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     uint32_t borrow = sub_q(s, v);
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = borrow ? v[i] : s[i];
+#endif
 }
 
 // r = v / 2^32 mod q for a 9-limb v < 2^32 * q (one Montgomery step; used after small-integer linear maps)

@@ -5,16 +5,21 @@
 // so every warp access is a run of 128-bit vector loads.  There is deliberately no CPU path.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/jjschnorr_b200.h"
 #include "multisig_core.cuh"
 #include "sign_core.cuh"
 #include "verify_core.cuh"
+#include "fqs.cuh"
+#include "safe_tag.h"
 
 namespace tables {
 #include "jjs_constants_tables.h"
@@ -86,27 +91,100 @@ __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_points_to_ext(cons
     }
 }
 
-// one thread hashes the delinearisation coefficients of one item's signer keys (same item order as k_aggregate)
+// ---- aggregate-key path: ordering of a chunk by signer count, entirely on the device -----------------------------------
+// Items are bucketed by signer count (bucket 64 collects everything above 63) so that the lanes of a warp hash transcripts
+// of one length and fold the same number of keys.  Three small kernels replace the host-side counting sort of round 1 (and
+// the stream synchronisation it needed): histogram, exclusive scan over the 65 buckets, scatter.  The order inside a bucket
+// depends on atomics; results are written by item index, so the outputs do not.
+constexpr int AGG_BUCKETS = 65;
+struct AggSort {
+    uint32_t hist[AGG_BUCKETS], khist[AGG_BUCKETS];    // items / keys per bucket
+    uint32_t ibase[AGG_BUCKETS], kbase[AGG_BUCKETS];   // first sorted item / key position of the bucket
+    uint32_t cursor[AGG_BUCKETS], kcursor;             // scatter cursors (kcursor: keys of the open-ended bucket)
+};
+__global__ void __launch_bounds__(BLOCK) k_agg_hist(const uint32_t* offsets, size_t n, AggSort* c) {
+    __shared__ uint32_t h[AGG_BUCKETS], kh[AGG_BUCKETS];
+    for (int i = threadIdx.x; i < AGG_BUCKETS; i += blockDim.x) { h[i] = 0; kh[i] = 0; }
+    __syncthreads();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t cnt = offsets[i + 1] - offsets[i], b = cnt < AGG_BUCKETS - 1 ? cnt : AGG_BUCKETS - 1;
+        atomicAdd(&h[b], 1u);
+        atomicAdd(&kh[b], cnt);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < AGG_BUCKETS; k += blockDim.x) {
+        if (h[k]) atomicAdd(&c->hist[k], h[k]);
+        if (kh[k]) atomicAdd(&c->khist[k], kh[k]);
+    }
+}
+__global__ void k_agg_scan(AggSort* c) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t ib = 0, kb = 0;
+    for (int b = 0; b < AGG_BUCKETS; b++) {
+        c->ibase[b] = ib;
+        c->kbase[b] = kb;
+        ib += c->hist[b];
+        kb += c->khist[b];
+    }
+}
+// order[p]: item at sorted position p;  kmap[q] / kitem[q]: key (relative to the chunk's first key) and item at sorted key position q
+__global__ void __launch_bounds__(BLOCK) k_agg_scatter(const uint32_t* offsets, uint32_t key_base, size_t n, AggSort* c, uint32_t* order, uint32_t* kmap,
+                                                       uint32_t* kitem) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t lo = 0, cnt = 0, b = 0xffffffffu;
+    if (valid) {
+        lo = offsets[i];
+        cnt = offsets[i + 1] - lo;
+        b = cnt < AGG_BUCKETS - 1 ? cnt : AGG_BUCKETS - 1;
+    }
+    // one atomic per distinct bucket of the warp
+    const int lane = threadIdx.x & 31;
+    uint32_t pos = 0;
+    uint32_t remaining = __ballot_sync(0xffffffffu, valid);
+    while (remaining) {
+        int leader = __ffs(remaining) - 1;
+        uint32_t bb = __shfl_sync(0xffffffffu, b, leader);
+        uint32_t grp = __ballot_sync(0xffffffffu, valid && b == bb);
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&c->cursor[bb], (uint32_t)__popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid && b == bb) pos = base + __popc(grp & ((1u << lane) - 1u));
+        remaining &= ~grp;
+    }
+    if (!valid) return;
+    order[c->ibase[b] + pos] = (uint32_t)i;
+    uint32_t kpos = b < AGG_BUCKETS - 1 ? c->kbase[b] + pos * cnt : c->kbase[b] + atomicAdd(&c->kcursor, cnt);
+    for (uint32_t j = 0; j < cnt; j++) {
+        kmap[kpos + j] = lo - key_base + j;
+        kitem[kpos + j] = (uint32_t)i;
+    }
+}
+
+// one thread hashes the delinearisation coefficient of ONE signer key (sorted key order: the threads of a warp hash transcripts of
+// one length).  Per key rather than per item: an item with n signers costs n hashes of 2 + 2 n elements, and spread over n
+// threads that work no longer depends on the signer count of the neighbouring items.
 __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_agg_coeffs(const fq* keys_u, const fq* keys_v, const uint8_t* kflags,
-                                                                          const uint32_t* offsets, const uint32_t* order, uint32_t key_base, size_t n,
-                                                                          uint32_t* d_words) {
+                                                                          const uint32_t* offsets, const uint32_t* kmap, const uint32_t* kitem,
+                                                                          uint32_t key_base, size_t n_keys, uint32_t* d_words, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    size_t item = order[t];
-    stage_aggregate_coeffs(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, d_words);
+    if (t >= n_keys) return;
+    size_t item = kitem[t];
+    stage_aggregate_coeff_key(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, kmap[t], d_words, T.safe_tags);
 }
 
 // one thread folds the signer keys of one item into its aggregate key (slot 0 of the single-variant point arrays)
 // `order` lists the items sorted by signer count, so the lanes of a warp loop over the same number of signers
 __global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, const uint32_t* offsets,
                                                      const uint32_t* order, uint32_t key_base, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags,
-                                                     uint8_t* agg_out, fq* tab, size_t stride, uint32_t* d_words) {
+                                                     uint8_t* agg_out, fq* tab, size_t stride, uint32_t* d_words, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     size_t item = order[t];
     uint32_t w[8];
     stage_aggregate(keys_u, keys_v, kflags, offsets[item] - key_base, offsets[item + 1] - key_base, pts_u, pts_v, pflags, item, w, tab + t, stride,
-                    d_words);
+                    T.safe_tags, d_words);
     if (agg_out) {
         uint4* o = reinterpret_cast<uint4*>(agg_out + item * 32);
         o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -179,6 +257,40 @@ __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int varian
         rlist[atomicAdd(rcount, 1u)] = (uint32_t)((size_t)r_slot * n + item);
     }
     eqflags[(size_t)eq * n + item] = ok ? 1 : 0;
+}
+
+// The same stage on the slot-based evaluation (fqs.cuh): field elements in shared memory, addressed by handle, so that no
+// product needs its operands marshalled through registers.  Persistent: the grid is one wave of resident CTAs and every
+// thread walks the work list with the grid's stride, which lets the two per-thread tables live in a scratch indexed by
+// RESIDENT thread (gridDim.x * blockDim.x threads x 2 KiB, L2 sized) instead of by item.
+#ifndef JJS_EQ2_MINBLOCKS
+#define JJS_EQ2_MINBLOCKS 4
+#endif
+#ifndef JJS_EQ_V2
+#define JJS_EQ_V2 0   // measured (profiles/r02_*): the register-operand kernel is 4-7 % faster; the slot-based one stays as a tested alternative
+#endif
+__global__ void __launch_bounds__(JJS_EQ_BLOCK, JJS_EQ2_MINBLOCKS) k_equation2(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n,
+                                                                                const uint32_t* list, const uint32_t* lcount, WireField usc,
+                                                                                const uint32_t* cwords, uint8_t* eqflags, fq* tab, Tables T,
+                                                                                uint32_t* rlist, uint32_t* rcount) {
+    const Eq2Slots s = eq2_slots(threadIdx.x);
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int neq = variant == VAR_DOUBLE ? 2 : 1;
+    const size_t total = (size_t)neq * *lcount;
+#pragma unroll 1
+    for (size_t g = tid; g < total; g += nthreads) {
+        int eq = (int)(g % neq);
+        size_t item = list[g / neq];
+        bool need_r_test;
+        bool ok = eq2_equation_item(s, variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
+                                    tab + tid, tab + EQ2_TAB_FQ * nthreads + tid, nthreads, &need_r_test);
+        if (need_r_test) {
+            int pk_slot, r_slot, base_slot;
+            equation_slots(variant, eq, pk_slot, r_slot, base_slot);
+            rlist[atomicAdd(rcount, 1u)] = (uint32_t)((size_t)r_slot * n + item);
+        }
+        eqflags[(size_t)eq * n + item] = ok ? 1 : 0;
+    }
 }
 
 // deferred subgroup tests: thread t < *rcount tests point rlist[t]
@@ -264,12 +376,12 @@ struct MsigBuffers {
     const uint32_t *offsets, *owner, *order;
 };
 
-__global__ void __launch_bounds__(BLOCK) k_msig_session(MsigBuffers b, size_t K, size_t n, WireField msg, WireField zf, fq* tab, size_t stride) {
+__global__ void __launch_bounds__(BLOCK) k_msig_session(MsigBuffers b, size_t K, size_t n, WireField msg, WireField zf, fq* tab, size_t stride, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     size_t s = b.order[t];
     stage_msig_session(b.pu, b.pv, b.pf, K, b.offsets[s], b.offsets[s + 1], msg, zf, s, b.d_words, b.cd_words, b.a_words, b.rsa_u, b.rsa_v, b.sflags,
-                       tab + t, stride);
+                       tab + t, stride, T.safe_tags);
 }
 __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_msig_share(MsigBuffers b, size_t K, WireField zf, fq* tab, size_t stride, Tables T) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,6 +463,14 @@ __global__ void __launch_bounds__(BLOCK) k_sign_aggregate(const uint8_t* sk, con
     for (int k = 0; k < 4; k++) so[k] = ok ? make_uint4(sig[4 * k], sig[4 * k + 1], sig[4 * k + 2], sig[4 * k + 3]) : make_uint4(0, 0, 0, 0);
 }
 
+struct AggScratch {   // aggregate-key path, one per scratch half: decoded signer keys, their coefficients, the sorted orders
+    fq *keys_u = nullptr, *keys_v = nullptr;
+    uint8_t* kflags = nullptr;
+    uint32_t *kcoef = nullptr, *kmap = nullptr, *kitem = nullptr, *order = nullptr;
+    AggSort* sort = nullptr;
+    size_t cap_keys = 0;
+};
+
 struct DeviceState {
     int device = -1;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -363,41 +483,44 @@ struct DeviceState {
     uint8_t* dlog_hash = nullptr;
     niels* fb_g = nullptr;
     niels* fb_gn = nullptr;
+    fq* safe_tags = nullptr;     // SAFE tags by number of absorbed elements (multisig transcripts of run-time length)
+    size_t n_tags = 0;
     // pipeline scratch, sized for CHUNK_ITEMS items of the widest variant (4 points, 2 equations)
     fq *pts_u = nullptr, *pts_v = nullptr, *tab = nullptr;
     uint8_t *pflags = nullptr, *iflags = nullptr, *eqflags = nullptr;
     uint32_t* cwords = nullptr;
     uint32_t *rlist = nullptr, *rcount = nullptr;  // signature points awaiting the deferred subgroup test
     uint32_t* eqlist = nullptr;                    // items that go on to the hash and equation kernels (k_work_list)
-    // decoded signer keys of the aggregate-key path (grown on demand)
-    fq *keys_u = nullptr, *keys_v = nullptr;
-    uint8_t* kflags = nullptr;
-    uint32_t* kcoef = nullptr;     // delinearisation coefficients, 8 words per key
-    size_t cap_keys = 0;
-    uint32_t* d_order = nullptr;   // items of a chunk sorted by signer count
-    std::vector<uint32_t> h_order;
-    uint8_t* agg_stage = nullptr;  // grow-only staging of the aggregate-key host path
-    size_t agg_stage_bytes = 0;
-    // staging for the host-buffer entry points
-    uint8_t *s_pk = nullptr, *s_sig = nullptr, *s_msg = nullptr, *s_status = nullptr, *s_c = nullptr;
-    uint32_t* s_bitmap = nullptr;
-    size_t stage_items = 0;
-    Tables tables() const { return Tables{root_tables, dlog_hash, fb_g, fb_gn}; }
+    // persistent equation kernel: one wave of resident CTAs, two per-thread tables per resident thread, one such scratch
+    // per compute stream (the two sub-chunk streams may run their equation kernels back to back or side by side)
+    fq* eqtab = nullptr;
+    int eq_grid = 0;
+    AggScratch agg[2];
+    // staging of the host-buffer entry points: one grow-only device buffer, carved up per call
+    uint8_t* stage = nullptr;
+    size_t stage_bytes = 0;
+    Tables tables() const { return Tables{root_tables, dlog_hash, fb_g, fb_gn, safe_tags}; }
 };
 
 // A slice of the pipeline scratch able to hold `cap` items of the widest variant; `tab` serves `cap` threads (the table
 // scratch keeps its global stride TAB_THREADS).
 struct Region {
-    fq *pts_u, *pts_v, *tab;
+    fq *pts_u, *pts_v, *tab, *eqtab;
     uint8_t *pflags, *iflags, *eqflags;
     uint32_t *cwords, *rlist, *rcount, *eqlist;   // rcount[0]: deferred subgroup tests, rcount[2]: length of the work list
     size_t cap;
+    int half;
 };
-inline Region region_of(const DeviceState& d, size_t first_item, size_t cap, int counter) {
-    return Region{d.pts_u + 4 * first_item, d.pts_v + 4 * first_item, d.tab + first_item, d.pflags + 4 * first_item, d.iflags + first_item,
-                  d.eqflags + 2 * first_item, d.cwords + 8 * first_item, d.rlist + 2 * first_item, d.rcount + counter, d.eqlist + 2 * first_item, cap};
+inline Region region_of(const DeviceState& d, size_t first_item, size_t cap, int half) {
+    return Region{d.pts_u + 4 * first_item, d.pts_v + 4 * first_item, d.tab + first_item,
+                  d.eqtab + (size_t)(half & 1) * 2 * EQ2_TAB_FQ * (size_t)d.eq_grid * JJS_EQ_BLOCK, d.pflags + 4 * first_item, d.iflags + first_item,
+                  d.eqflags + 2 * first_item, d.cwords + 8 * first_item, d.rlist + 2 * first_item, d.rcount + 4 * (half & 1), d.eqlist + 2 * first_item, cap,
+                  half & 1};
 }
+constexpr size_t SUB_ITEMS = CHUNK_ITEMS / 2;      // items per scratch half
+constexpr size_t SUB_CHUNK = size_t(1) << 18;      // items per sub-chunk of an overlapped batch
 inline Region region_whole(const DeviceState& d) { return region_of(d, 0, CHUNK_ITEMS, 0); }
+inline Region region_half(const DeviceState& d, size_t j) { return region_of(d, (j & 1) * SUB_ITEMS, SUB_ITEMS, (int)(j & 1)); }
 
 }  // namespace
 
@@ -409,16 +532,20 @@ struct StageRecord {
 
 struct jjs_ctx {
     std::vector<DeviceState> dev;
+    bool ready = false;              // jjs_init succeeded on every device; nothing else may touch the devices
+    std::mutex mu;                   // guards err and records (the host entry points run one worker thread per device)
     char err[512];
-    uint64_t launches;
-    bool profile;
+    std::atomic<uint64_t> launches{0};
+    bool profile = false;
     std::vector<StageRecord> records;
+    std::vector<fq> tags;            // host copy of the SAFE tag table
 };
 
 namespace {
 
 int fail(jjs_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
         va_list ap;
         va_start(ap, fmt);
         vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
@@ -432,6 +559,14 @@ int fail(jjs_ctx* ctx, int code, const char* fmt, ...) {
         cudaError_t e_ = (call);                                                                              \
         if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? JJS_ERR_NOMEM : JJS_ERR_CUDA, \
                                            "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// Every entry point starts here: a context whose jjs_init failed exists only so that the caller can read the reason.
+#define JJS_ENTER(ctx)                                                                                         \
+    do {                                                                                                      \
+        if (!(ctx)) return JJS_ERR_ARGUMENT;                                                                  \
+        if (!(ctx)->ready || (ctx)->dev.empty()) return JJS_ERR_CUDA; /* err keeps the message of jjs_init */ \
+        { std::lock_guard<std::mutex> lock_((ctx)->mu); (ctx)->err[0] = 0; }                                  \
     } while (0)
 
 // Optional per-stage timing: CUDA events recorded on the launching stream around each stage's launches.
@@ -450,11 +585,13 @@ struct StageTimer {
     void stop(cudaStream_t s) {
         if (!on) return;
         cudaEventRecord(rec.e1, s);
+        std::lock_guard<std::mutex> lock(ctx->mu);
         ctx->records.push_back(rec);
     }
 };
 
 inline unsigned blocks_for(size_t threads) { return (unsigned)((threads + BLOCK - 1) / BLOCK); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     if (d.pts_u) return JJS_SUCCESS;
@@ -466,26 +603,86 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaMalloc(&d.eqflags, 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.cwords, 32 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.rlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
-    JJS_CUDA(ctx, cudaMalloc(&d.rcount, 4 * sizeof(uint32_t)));
+    JJS_CUDA(ctx, cudaMalloc(&d.rcount, 8 * sizeof(uint32_t)));
     JJS_CUDA(ctx, cudaMalloc(&d.eqlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * AGG_GROUP * 36 * TAB_THREADS));
+    {
+        cudaDeviceProp prop;
+        JJS_CUDA(ctx, cudaGetDeviceProperties(&prop, d.device));
+        const size_t smem = sizeof(uint4) * 2 * EQ2_SLOTS * JJS_EQ_BLOCK;
+        JJS_CUDA(ctx, cudaFuncSetAttribute(k_equation2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JJS_CUDA(ctx, cudaFuncSetAttribute(k_equation2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0;
+        JJS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_equation2, JJS_EQ_BLOCK, smem));
+        if (per_sm < 1) return fail(ctx, JJS_ERR_CUDA, "k_equation2 does not fit on an SM of device %d", d.device);
+        d.eq_grid = per_sm * prop.multiProcessorCount;
+        JJS_CUDA(ctx, cudaMalloc(&d.eqtab, sizeof(fq) * 2 * 2 * EQ2_TAB_FQ * (size_t)d.eq_grid * JJS_EQ_BLOCK));
+    }
     return JJS_SUCCESS;
 }
 
-int ensure_staging(jjs_ctx* ctx, DeviceState& d, size_t items) {
-    if (items <= d.stage_items) return JJS_SUCCESS;
+// grow-only staging buffer of the host-buffer entry points; growing waits for the device (nothing of this context is in
+// flight at that point: the host entry points are synchronous)
+int ensure_stage(jjs_ctx* ctx, DeviceState& d, size_t bytes) {
+    if (bytes <= d.stage_bytes) return JJS_SUCCESS;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
-    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c); cudaFree(d.s_bitmap);
-    d.s_pk = d.s_sig = d.s_msg = d.s_status = d.s_c = nullptr;
-    d.s_bitmap = nullptr;
-    d.stage_items = 0;
-    JJS_CUDA(ctx, cudaMalloc(&d.s_pk, 64 * items));
-    JJS_CUDA(ctx, cudaMalloc(&d.s_sig, 96 * items));
-    JJS_CUDA(ctx, cudaMalloc(&d.s_msg, 32 * items));
-    JJS_CUDA(ctx, cudaMalloc(&d.s_status, items));
-    JJS_CUDA(ctx, cudaMalloc(&d.s_c, 32 * items));
-    JJS_CUDA(ctx, cudaMalloc(&d.s_bitmap, 4 * ((items + 31) / 32)));
-    d.stage_items = items;
+    JJS_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(d.stage);
+    d.stage = nullptr;
+    d.stage_bytes = 0;
+    JJS_CUDA(ctx, cudaMalloc(&d.stage, bytes));
+    d.stage_bytes = bytes;
+    return JJS_SUCCESS;
+}
+
+// SAFE tags up to `n_absorb` absorbed elements on device d (multisig transcripts).  The table is sized at jjs_init for
+// 1 024 elements (511 signers per aggregate key, 255 participants per session); a larger transcript grows it, which
+// waits for the device once.
+int ensure_tags(jjs_ctx* ctx, DeviceState& d, size_t n_absorb) {
+    if (n_absorb < d.n_tags) return JJS_SUCCESS;
+    size_t want = d.n_tags ? d.n_tags : 1024;
+    while (want <= n_absorb) want *= 2;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        while (ctx->tags.size() < want) {
+            fq t;
+            safe_tag_mont(t.l, (uint32_t)ctx->tags.size());
+            ctx->tags.push_back(t);
+        }
+    }
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    JJS_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(d.safe_tags);
+    d.safe_tags = nullptr;
+    d.n_tags = 0;
+    JJS_CUDA(ctx, cudaMalloc(&d.safe_tags, sizeof(fq) * want));
+    JJS_CUDA(ctx, cudaMemcpy(d.safe_tags, ctx->tags.data(), sizeof(fq) * want, cudaMemcpyHostToDevice));
+    d.n_tags = want;
+    return JJS_SUCCESS;
+}
+
+// key scratch of the aggregate path, both halves; growing waits for the device
+constexpr size_t AGG_KEYS_INITIAL = size_t(1) << 21;
+int ensure_agg_scratch(jjs_ctx* ctx, DeviceState& d, size_t keys) {
+    if (keys <= d.agg[0].cap_keys) return JJS_SUCCESS;
+    size_t want = d.agg[0].cap_keys ? d.agg[0].cap_keys : AGG_KEYS_INITIAL;
+    while (want < keys) want *= 2;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    JJS_CUDA(ctx, cudaDeviceSynchronize());
+    for (int h = 0; h < 2; h++) {
+        AggScratch& a = d.agg[h];
+        cudaFree(a.keys_u); cudaFree(a.keys_v); cudaFree(a.kflags); cudaFree(a.kcoef); cudaFree(a.kmap); cudaFree(a.kitem);
+        a.keys_u = a.keys_v = nullptr; a.kflags = nullptr; a.kcoef = a.kmap = a.kitem = nullptr; a.cap_keys = 0;
+        JJS_CUDA(ctx, cudaMalloc(&a.keys_u, sizeof(fq) * want));
+        JJS_CUDA(ctx, cudaMalloc(&a.keys_v, sizeof(fq) * want));
+        JJS_CUDA(ctx, cudaMalloc(&a.kflags, want));
+        JJS_CUDA(ctx, cudaMalloc(&a.kcoef, 32 * want));
+        JJS_CUDA(ctx, cudaMalloc(&a.kmap, sizeof(uint32_t) * want));
+        JJS_CUDA(ctx, cudaMalloc(&a.kitem, sizeof(uint32_t) * want));
+        if (!a.order) JJS_CUDA(ctx, cudaMalloc(&a.order, sizeof(uint32_t) * CHUNK_ITEMS));
+        if (!a.sort) JJS_CUDA(ctx, cudaMalloc(&a.sort, sizeof(AggSort)));
+        a.cap_keys = want;
+    }
     return JJS_SUCCESS;
 }
 
@@ -536,12 +733,23 @@ int enqueue_equations(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant
     Tables T = d.tables();
     StageTimer t3(ctx, d.device, 3, stream);
     JJS_CUDA(ctx, cudaMemsetAsync(R.rcount, 0, sizeof(uint32_t), stream));
+#if JJS_EQ_V2
+    {
+        const size_t smem = sizeof(uint4) * 2 * EQ2_SLOTS * JJS_EQ_BLOCK;
+        const size_t want = (neq * m + JJS_EQ_BLOCK - 1) / JJS_EQ_BLOCK;
+        const unsigned grid = (unsigned)(want < (size_t)d.eq_grid ? want : (size_t)d.eq_grid);
+        k_equation2<<<grid, JJS_EQ_BLOCK, smem, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, R.eqlist, R.rcount + 2, fu, R.cwords, R.eqflags,
+                                                         R.eqtab, T, R.rlist, R.rcount);
+        ctx->launches++;
+    }
+#else
     for (size_t first = 0; first < neq * m; first += R.cap) {
         size_t cnt = neq * m - first < R.cap ? neq * m - first : R.cap;
         k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, first, cnt, R.eqlist, R.rcount + 2, fu, R.cwords,
                                                          R.eqflags, R.tab, TAB_THREADS, T, R.rlist, R.rcount);
         ctx->launches++;
     }
+#endif
     t3.stop(stream);
     StageTimer t5(ctx, d.device, 5, stream);
     k_rtest<<<blocks_for(neq * m), BLOCK, 0, stream>>>(R.pts_u, R.pts_v, R.pflags, R.rlist, R.rcount);
@@ -577,297 +785,429 @@ int run_chunk(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant, const 
     return JJS_SUCCESS;
 }
 
-constexpr size_t SUB_ITEMS = CHUNK_ITEMS / 2;      // items per scratch half
-constexpr size_t SUB_CHUNK = size_t(1) << 18;      // items per sub-chunk of an overlapped batch
+// Typed inputs: the same pipeline behind k_decode_ext (points as JubJubExtended coordinates, 160 bytes each, item-major).
+int run_chunk_ext(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant, const uint8_t* pts, const uint8_t* u32, const uint8_t* msg, size_t m,
+                  uint8_t* status, uint8_t* c_out, cudaStream_t stream) {
+    const int slots = variant_slots(variant);
+    WireField fmsg{msg, 32}, fu{u32, 32};
+    StageTimer t0(ctx, d.device, 0, stream);
+    k_decode_ext<<<blocks_for(slots * m), BLOCK, 0, stream>>>(pts, slots, m, R.pts_u, R.pts_v, R.pflags, key_slot_mask(variant));
+    t0.stop(stream);
+    ctx->launches++;
+    int rc = enqueue_challenges(ctx, d, R, variant, m, fmsg, fu, stream, true);
+    if (!rc) rc = enqueue_equations(ctx, d, R, variant, m, fu, stream);
+    if (rc) return rc;
+    k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(variant, R.pflags, R.iflags, R.eqflags, R.cwords, m, status, c_out);
+    ctx->launches++;
+    return JJS_SUCCESS;
+}
+
+// aggregate_pk(..).verify(..) for one chunk of m <= R.cap items with K <= cap_keys signer keys; everything on `stream`,
+// nothing on the host.  d_keys: the chunk's first key; d_offsets: the chunk's m + 1 offsets (absolute, first = key_lo).
+int run_chunk_aggregate(jjs_ctx* ctx, DeviceState& d, const Region& R, const uint8_t* d_keys, const uint32_t* d_offsets, uint32_t key_lo, size_t K,
+                        const uint8_t* d_sig, const uint8_t* d_msg, size_t m, uint8_t* d_status, uint8_t* d_c, uint8_t* d_agg, cudaStream_t stream) {
+    AggScratch& A = d.agg[R.half];
+    Tables T = d.tables();
+    Fields fk, fr;
+    fk.f[0] = WireField{d_keys, 32};
+    fr.f[0] = WireField{d_sig + 32, 64};
+    fk.f[1] = fk.f[2] = fk.f[3] = fr.f[1] = fr.f[2] = fr.f[3] = WireField{nullptr, 0};
+    WireField fmsg{d_msg, 32}, fu{d_sig, 64};
+    StageTimer t0(ctx, d.device, 0, stream);
+    if (K) k_decode<<<blocks_for(K), BLOCK, 0, stream>>>(fk, 1, 0, K, A.keys_u, A.keys_v, A.kflags, T, 0u);
+    k_decode<<<blocks_for(m), BLOCK, 0, stream>>>(fr, 1, 1, m, R.pts_u, R.pts_v, R.pflags, T, 0u);
+    t0.stop(stream);
+    StageTimer t2(ctx, d.device, 2, stream);
+    JJS_CUDA(ctx, cudaMemsetAsync(A.sort, 0, sizeof(AggSort), stream));
+    k_agg_hist<<<blocks_for(m), BLOCK, 0, stream>>>(d_offsets, m, A.sort);
+    k_agg_scan<<<1, 32, 0, stream>>>(A.sort);
+    k_agg_scatter<<<blocks_for(m), BLOCK, 0, stream>>>(d_offsets, key_lo, m, A.sort, A.order, A.kmap, A.kitem);
+    if (K) k_agg_coeffs<<<blocks_for(K), BLOCK, 0, stream>>>(A.keys_u, A.keys_v, A.kflags, d_offsets, A.kmap, A.kitem, key_lo, K, A.kcoef, T);
+    k_aggregate<<<blocks_for(m), BLOCK, 0, stream>>>(A.keys_u, A.keys_v, A.kflags, d_offsets, A.order, key_lo, m, R.pts_u, R.pts_v, R.pflags, d_agg, R.tab,
+                                                    TAB_THREADS, A.kcoef, T);
+    t2.stop(stream);
+    ctx->launches += 7;
+    int rc = enqueue_challenges(ctx, d, R, VAR_SINGLE, m, fmsg, fu, stream, true);
+    if (!rc) rc = enqueue_equations(ctx, d, R, VAR_SINGLE, m, fu, stream);
+    if (rc) return rc;
+    StageTimer t4(ctx, d.device, 4, stream);
+    k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, R.pflags, R.iflags, R.eqflags, R.cwords, m, d_status, d_c);
+    t4.stop(stream);
+    ctx->launches++;
+    return JJS_SUCCESS;
+}
+
+// Sub-chunks of an overlapped batch alternate between the two internal streams and scratch halves: kernels of neighbouring
+// sub-chunks overlap, which hides the partially filled last wave of every launch (per-thread work is uniform, so a launch
+// ends with SMs idling for up to one block duration).  With per-stage profiling on, everything stays on `stream` so that
+// the stage timers do not overlap.
+struct Overlap {
+    jjs_ctx* ctx;
+    DeviceState& d;
+    cudaStream_t stream;
+    bool on;
+    size_t i = 0;
+    Overlap(jjs_ctx* c, DeviceState& dev, cudaStream_t s, bool enable) : ctx(c), d(dev), stream(s), on(enable && !c->profile) {}
+    int begin() {
+        if (!on) return JJS_SUCCESS;
+        JJS_CUDA(ctx, cudaEventRecord(d.fork, stream));
+        for (int k = 0; k < 2; k++) JJS_CUDA(ctx, cudaStreamWaitEvent(d.sub[k], d.fork, 0));
+        return JJS_SUCCESS;
+    }
+    cudaStream_t next_stream() const { return on ? d.sub[i & 1] : stream; }
+    Region next_region() const { return on ? region_half(d, i) : region_whole(d); }
+    void advance() { i++; }
+    int end() {
+        if (!on) return JJS_SUCCESS;
+        for (int k = 0; k < 2; k++) {
+            JJS_CUDA(ctx, cudaEventRecord(d.join[k], d.sub[k]));
+            JJS_CUDA(ctx, cudaStreamWaitEvent(stream, d.join[k], 0));
+        }
+        return JJS_SUCCESS;
+    }
+};
 
 // Enqueue the whole pipeline for n items (device pointers); the work is ordered after what `stream` holds now and
-// `stream` waits for it.  Batches above one sub-chunk are cut into sub-chunks that alternate between the two internal
-// streams and scratch halves: kernels of neighbouring sub-chunks overlap, which hides the partially filled last wave
-// of every launch (per-thread work is uniform, so a launch ends with SMs idling for up to one block duration).
-// With per-stage profiling on, everything stays on `stream` so that the stage timers do not overlap.
+// `stream` waits for it.
 int run_device(jjs_ctx* ctx, DeviceState& d, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
                uint8_t* status, uint8_t* c_out, cudaStream_t stream, bool challenge_only = false) {
     int rc = ensure_scratch(ctx, d);
     if (rc) return rc;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
-    const bool overlap = !ctx->profile && n > SUB_CHUNK;
-    if (overlap) {
-        JJS_CUDA(ctx, cudaEventRecord(d.fork, stream));
-        for (int k = 0; k < 2; k++) JJS_CUDA(ctx, cudaStreamWaitEvent(d.sub[k], d.fork, 0));
-    }
-    const size_t step = overlap ? SUB_CHUNK : CHUNK_ITEMS;
-    size_t i = 0;
-    for (size_t off = 0; off < n; off += step, i++) {
+    Overlap ov(ctx, d, stream, n > SUB_CHUNK);
+    rc = ov.begin();
+    if (rc) return rc;
+    const size_t step = ov.on ? SUB_CHUNK : CHUNK_ITEMS;
+    for (size_t off = 0; off < n; off += step, ov.advance()) {
         size_t m = n - off < step ? n - off : step;
-        Region R = overlap ? region_of(d, (i & 1) * SUB_ITEMS, SUB_ITEMS, (int)(i & 1)) : region_whole(d);
-        rc = run_chunk(ctx, d, R, variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, m,
-                       status ? status + off : nullptr, c_out ? c_out + off * 32 : nullptr, overlap ? d.sub[i & 1] : stream, challenge_only);
+        rc = run_chunk(ctx, d, ov.next_region(), variant, pk + off * pk_size(variant), sig + off * sig_size(variant), msg + off * 32, m,
+                       status ? status + off : nullptr, c_out ? c_out + off * 32 : nullptr, ov.next_stream(), challenge_only);
         if (rc) return rc;
     }
-    if (overlap)
-        for (int k = 0; k < 2; k++) {
-            JJS_CUDA(ctx, cudaEventRecord(d.join[k], d.sub[k]));
-            JJS_CUDA(ctx, cudaStreamWaitEvent(stream, d.join[k], 0));
-        }
+    rc = ov.end();
+    if (rc) return rc;
     JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
 }
 
-// Host-buffer path: contiguous shards over the context's devices, one stream each, joined before return.
-int run_host(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status,
-             uint8_t* c_out, bool challenge_only = false, uint32_t* bitmap = nullptr) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
-    if (n == 0) return JJS_SUCCESS;
-    if (!pk || !sig || !msg || (!status && !challenge_only && !bitmap) || (challenge_only && !c_out)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
-    const size_t g = ctx->dev.size();
-    const size_t per = ((n + g - 1) / g + 31) & ~size_t(31);  // shards start on a bitmap word
-    const size_t pks = pk_size(variant), sgs = sig_size(variant);
-    // Each device's shard is cut into pipeline slices: slice j + 1 is copied in on the copy stream while slice j is
-    // being verified (the kernels of one slice run far longer than its 128-192 B/item copy), and consecutive slices
-    // alternate between the two internal compute streams and scratch halves, like the sub-chunks of run_device.
-    // The first slice is short so that compute starts early.
-    for (size_t k = 0; k < g; k++) {
-        size_t lo = k * per, hi = lo + per < n ? lo + per : n;
-        if (lo >= hi) break;
-        DeviceState& d = ctx->dev[k];
-        size_t m = hi - lo;
-        int rc = ensure_staging(ctx, d, m);
-        if (!rc) rc = ensure_scratch(ctx, d);
-        if (rc) return rc;
-        JJS_CUDA(ctx, cudaSetDevice(d.device));
-        uint8_t* dc = (c_out || challenge_only) ? d.s_c : nullptr;
-        const bool serial = ctx->profile;  // stage timers must not overlap
-        size_t j = 0;
-        for (size_t off = 0; off < m; j++) {
-            size_t want = j == 0 ? SUB_CHUNK / 4 : SUB_CHUNK;
-            size_t cnt = m - off < want ? m - off : want;
-            JJS_CUDA(ctx, cudaMemcpyAsync(d.s_pk + off * pks, pk + (lo + off) * pks, cnt * pks, cudaMemcpyHostToDevice, d.copy_stream));
-            JJS_CUDA(ctx, cudaMemcpyAsync(d.s_sig + off * sgs, sig + (lo + off) * sgs, cnt * sgs, cudaMemcpyHostToDevice, d.copy_stream));
-            JJS_CUDA(ctx, cudaMemcpyAsync(d.s_msg + off * 32, msg + (lo + off) * 32, cnt * 32, cudaMemcpyHostToDevice, d.copy_stream));
-            JJS_CUDA(ctx, cudaEventRecord(d.copied, d.copy_stream));
-            cudaStream_t cs = serial ? d.stream : d.sub[j & 1];
-            JJS_CUDA(ctx, cudaStreamWaitEvent(cs, d.copied, 0));
-            Region R = region_of(d, (j & 1) * SUB_ITEMS, SUB_ITEMS, (int)(j & 1));
-            rc = run_chunk(ctx, d, R, variant, d.s_pk + off * pks, d.s_sig + off * sgs, d.s_msg + off * 32, cnt, d.s_status + off,
-                           dc ? dc + off * 32 : nullptr, cs, challenge_only);
-            if (rc) return rc;
-            off += cnt;
-        }
-        if (!serial)
-            for (int q = 0; q < 2; q++) {
-                JJS_CUDA(ctx, cudaEventRecord(d.join[q], d.sub[q]));
-                JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.join[q], 0));
-            }
-        if (!challenge_only && status) JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, d.s_status, m, cudaMemcpyDeviceToHost, d.stream));
-        if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + lo * 32, d.s_c, m * 32, cudaMemcpyDeviceToHost, d.stream));
-        if (bitmap) {
-            k_bitmap<<<blocks_for(m), BLOCK, 0, d.stream>>>(d.s_status, m, d.s_bitmap);
-            ctx->launches++;
-            JJS_CUDA(ctx, cudaMemcpyAsync(bitmap + lo / 32, d.s_bitmap, 4 * ((m + 31) / 32), cudaMemcpyDeviceToHost, d.stream));
-        }
+// Chunks of an aggregate-key batch: at most `max_items` items and `max_keys` signer keys each (an item with more keys than
+// that forms a chunk of its own, for which the caller grows the key scratch first).
+inline size_t agg_chunk_end(const uint32_t* offsets, size_t first, size_t n, size_t max_items, size_t max_keys) {
+    size_t end = first;
+    while (end < n && end - first < max_items && (size_t)(offsets[end + 1] - offsets[first]) <= max_keys) end++;
+    return end == first ? first + 1 : end;
+}
+inline size_t agg_max_item_keys(const uint32_t* offsets, size_t n) {
+    size_t mx = 0;
+    for (size_t i = 0; i < n; i++) {
+        size_t c = offsets[i + 1] - offsets[i];
+        if (c > mx) mx = c;
     }
-    for (size_t k = 0; k < g; k++) {
-        JJS_CUDA(ctx, cudaSetDevice(ctx->dev[k].device));
-        JJS_CUDA(ctx, cudaStreamSynchronize(ctx->dev[k].stream));
-    }
-    return JJS_SUCCESS;
+    return mx;
 }
 
 // aggregate_pk(..).verify(..) for n items whose wire data already sits on the device.  `h_offsets` is the host copy of
-// the n + 1 offsets (needed to plan the chunks); d_offsets the same array on the device.
+// the n + 1 offsets (it plans the chunks and sizes the tag table; it is read during the call only); d_offsets the same
+// array on the device.  Enqueue-only unless a scratch has to grow (first call, or more keys / signers than ever before).
 int run_aggregate_device(jjs_ctx* ctx, DeviceState& d, const uint8_t* d_pks, const uint32_t* d_offsets, const uint32_t* h_offsets,
                          const uint8_t* d_sig, const uint8_t* d_msg, size_t n, uint8_t* d_status, uint8_t* d_c, uint8_t* d_agg,
                          cudaStream_t stream) {
     int rc = ensure_scratch(ctx, d);
+    const size_t max_cnt = agg_max_item_keys(h_offsets, n);
+    if (!rc) rc = ensure_tags(ctx, d, 2 + 2 * max_cnt);
+    if (!rc) rc = ensure_agg_scratch(ctx, d, max_cnt > AGG_KEYS_INITIAL ? max_cnt : AGG_KEYS_INITIAL);
     if (rc) return rc;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
-    Tables T = d.tables();
-    for (size_t off = 0; off < n; off += CHUNK_ITEMS) {
-        size_t m = n - off < CHUNK_ITEMS ? n - off : CHUNK_ITEMS;
-        uint32_t key_lo = h_offsets[off], key_hi = h_offsets[off + m];
-        size_t K = key_hi - key_lo;
-        if (K > d.cap_keys) {
-            JJS_CUDA(ctx, cudaStreamSynchronize(stream));
-            cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.kcoef);
-            d.keys_u = d.keys_v = nullptr; d.kflags = nullptr; d.kcoef = nullptr; d.cap_keys = 0;
-            JJS_CUDA(ctx, cudaMalloc(&d.keys_u, sizeof(fq) * K));
-            JJS_CUDA(ctx, cudaMalloc(&d.keys_v, sizeof(fq) * K));
-            JJS_CUDA(ctx, cudaMalloc(&d.kflags, K));
-            JJS_CUDA(ctx, cudaMalloc(&d.kcoef, 32 * K));
-            d.cap_keys = K;
-        }
-        Fields fk, fr;
-        fk.f[0] = WireField{d_pks + 32 * (size_t)key_lo, 32};
-        fr.f[0] = WireField{d_sig + 64 * off + 32, 64};
-        fk.f[1] = fk.f[2] = fk.f[3] = fr.f[1] = fr.f[2] = fr.f[3] = WireField{nullptr, 0};
-        WireField fmsg{d_msg + 32 * off, 32}, fu{d_sig + 64 * off, 64};
-        StageTimer t0(ctx, d.device, 0, stream);
-        if (K) k_decode<<<blocks_for(K), BLOCK, 0, stream>>>(fk, 1, 0, K, d.keys_u, d.keys_v, d.kflags, T, 0u);
-        k_decode<<<blocks_for(m), BLOCK, 0, stream>>>(fr, 1, 1, m, d.pts_u, d.pts_v, d.pflags, T, 0u);
-        t0.stop(stream);
-        // counting sort of the chunk's items by signer count (host side; counts above 63 share the last bucket)
-        {
-            size_t hist[65] = {0};
-            for (size_t i = 0; i < m; i++) {
-                uint32_t c = h_offsets[off + i + 1] - h_offsets[off + i];
-                hist[(c > 63 ? 63 : c) + 1]++;
-            }
-            for (int b = 0; b < 64; b++) hist[b + 1] += hist[b];
-            d.h_order.resize(m);
-            for (size_t i = 0; i < m; i++) {
-                uint32_t c = h_offsets[off + i + 1] - h_offsets[off + i];
-                d.h_order[hist[c > 63 ? 63 : c]++] = (uint32_t)i;
-            }
-            if (!d.d_order) JJS_CUDA(ctx, cudaMalloc(&d.d_order, sizeof(uint32_t) * CHUNK_ITEMS));
-            JJS_CUDA(ctx, cudaStreamSynchronize(stream));  // h_order is reused by the next chunk / call
-            JJS_CUDA(ctx, cudaMemcpyAsync(d.d_order, d.h_order.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, stream));
-        }
-        StageTimer t2(ctx, d.device, 2, stream);
-        k_agg_coeffs<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, d.d_order, key_lo, m, d.kcoef);
-        k_aggregate<<<blocks_for(m), BLOCK, 0, stream>>>(d.keys_u, d.keys_v, d.kflags, d_offsets + off, d.d_order, key_lo, m, d.pts_u, d.pts_v,
-                                                        d.pflags, d_agg ? d_agg + 32 * off : nullptr, d.tab, TAB_THREADS, d.kcoef);
-        t2.stop(stream);
-        int rc2 = enqueue_challenges(ctx, d, region_whole(d), VAR_SINGLE, m, fmsg, fu, stream, true);
-        if (!rc2) rc2 = enqueue_equations(ctx, d, region_whole(d), VAR_SINGLE, m, fu, stream);
-        if (rc2) return rc2;
-        StageTimer t4(ctx, d.device, 4, stream);
-        k_finalize<<<blocks_for(m), BLOCK, 0, stream>>>(VAR_SINGLE, d.pflags, d.iflags, d.eqflags, d.cwords, m, d_status + off,
-                                                       d_c ? d_c + 32 * off : nullptr);
-        t4.stop(stream);
-        ctx->launches += 5;   // two decodes, the two aggregation kernels, finalize (the helpers count their own)
+    Overlap ov(ctx, d, stream, n > SUB_CHUNK);
+    rc = ov.begin();
+    if (rc) return rc;
+    const size_t step = ov.on ? SUB_CHUNK : SUB_ITEMS;
+    for (size_t off = 0; off < n; ov.advance()) {
+        size_t end = agg_chunk_end(h_offsets, off, n, step, d.agg[0].cap_keys);
+        size_t m = end - off;
+        uint32_t key_lo = h_offsets[off];
+        size_t K = h_offsets[end] - key_lo;
+        Region R = ov.on ? ov.next_region() : region_half(d, 0);
+        rc = run_chunk_aggregate(ctx, d, R, d_pks + 32 * (size_t)key_lo, d_offsets + off, key_lo, K, d_sig + 64 * off, d_msg + 32 * off, m, d_status + off,
+                                 d_c ? d_c + 32 * off : nullptr, d_agg ? d_agg + 32 * off : nullptr, ov.next_stream());
+        if (rc) return rc;
+        off = end;
     }
+    rc = ov.end();
+    if (rc) return rc;
     JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
 }
 
-// host buffers: contiguous shards over the devices, each shard copied to temporary device buffers
-int run_aggregate(jjs_ctx* ctx, const uint8_t* pks, const uint32_t* offsets, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status,
-                  uint8_t* c_out, uint8_t* agg_out) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
-    if (n == 0) return JJS_SUCCESS;
-    if (!offsets || !sig || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
-    for (size_t i = 0; i < n; i++)
-        if (offsets[i + 1] < offsets[i]) return fail(ctx, JJS_ERR_ARGUMENT, "offsets must be non-decreasing");
-    if (offsets[n] > offsets[0] && !pks) return fail(ctx, JJS_ERR_ARGUMENT, "null key buffer");
-    const size_t g = ctx->dev.size();
-    const size_t per = (n + g - 1) / g;
-    int rc = JJS_SUCCESS;
-    for (size_t k = 0; k < g && rc == JJS_SUCCESS; k++) {
-        size_t lo = k * per, hi = lo + per < n ? lo + per : n;
-        if (lo >= hi) break;
-        DeviceState& d = ctx->dev[k];
-        size_t m = hi - lo, K = offsets[hi] - offsets[lo];
-        cudaSetDevice(d.device);
-        // layout: keys | sig | msg | status(+pad) | c | agg | offsets
-        size_t o_sig = 32 * K, o_msg = o_sig + 64 * m, o_st = o_msg + 32 * m, o_c = o_st + ((m + 31) / 32) * 32, o_agg = o_c + 32 * m,
-               o_off = o_agg + 32 * m, total = o_off + 4 * (m + 1);
-        if (total > d.agg_stage_bytes) {
-            cudaStreamSynchronize(d.stream);
-            cudaFree(d.agg_stage);
-            d.agg_stage = nullptr;
-            d.agg_stage_bytes = 0;
-            cudaError_t e = cudaMalloc(&d.agg_stage, total);
-            if (e != cudaSuccess) { rc = fail(ctx, JJS_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
-            d.agg_stage_bytes = total;
-        }
-        uint8_t* b = d.agg_stage;
-        if (K) cudaMemcpyAsync(b, pks + 32 * (size_t)offsets[lo], 32 * K, cudaMemcpyHostToDevice, d.stream);
-        cudaMemcpyAsync(b + o_sig, sig + 64 * lo, 64 * m, cudaMemcpyHostToDevice, d.stream);
-        cudaMemcpyAsync(b + o_msg, msg + 32 * lo, 32 * m, cudaMemcpyHostToDevice, d.stream);
-        cudaMemcpyAsync(b + o_off, offsets + lo, 4 * (m + 1), cudaMemcpyHostToDevice, d.stream);
-        // device keys start at offsets[lo]: hand the kernels a key pointer that makes absolute offsets valid
-        rc = run_aggregate_device(ctx, d, b - 32 * (size_t)offsets[lo], reinterpret_cast<uint32_t*>(b + o_off), offsets + lo, b + o_sig, b + o_msg, m,
-                                  b + o_st, c_out ? b + o_c : nullptr, agg_out ? b + o_agg : nullptr, d.stream);
-        if (rc) break;
-        cudaMemcpyAsync(status + lo, b + o_st, m, cudaMemcpyDeviceToHost, d.stream);
-        if (c_out) cudaMemcpyAsync(c_out + 32 * lo, b + o_c, 32 * m, cudaMemcpyDeviceToHost, d.stream);
-        if (agg_out) cudaMemcpyAsync(agg_out + 32 * lo, b + o_agg, 32 * m, cudaMemcpyDeviceToHost, d.stream);
+// ---- host-buffer entry points ---------------------------------------------------------------------------------------------
+// A call verifies one or more PARTS (each a homogeneous batch: one of the three wire variants, aggregate-key items, or typed
+// items).  Every part is cut into contiguous shards, one per device of the context (small parts go whole to the least
+// loaded device), and every device is driven by its own host thread: copies in on the copy stream, pipeline slices alternating
+// between the two compute streams, results copied out at the end, one synchronisation.  A single host thread would serialise
+// the devices whenever the caller's memory is pageable (cudaMemcpyAsync from pageable memory returns only after staging).
+enum PartMode : int { PART_WIRE = 0, PART_AGGREGATE = 1, PART_TYPED = 2 };
+struct HostPart {
+    int mode, variant;
+    const uint8_t *pk, *sig, *msg;    // typed: pk = points_ext160, sig = u32
+    const uint32_t* offsets;          // aggregate only
+    size_t n;
+    uint8_t *status, *c_out, *agg_out;
+    uint32_t* bitmap;
+    bool challenge_only;
+};
+struct Shard {
+    size_t lo, hi;
+};
+
+inline double part_weight(const HostPart& p) {   // relative cost of one item (executed multiplies, single = 1)
+    if (p.mode == PART_AGGREGATE) {
+        double avg = p.n ? (double)(p.offsets[p.n] - p.offsets[0]) / (double)p.n : 0.0;
+        return 1.0 + 0.75 * avg;
     }
-    for (size_t k = 0; k < g; k++) {
+    return p.variant == VAR_DOUBLE ? 1.9 : (p.variant == VAR_VARGEN ? 1.45 : 1.0);
+}
+
+// shards[part][device].  Large parts are split evenly (every device then carries the same share of every kind, so the
+// devices finish together whatever the mix); parts too small to be worth splitting go whole to the least loaded device.
+constexpr size_t MIN_SPLIT_ITEMS = 8192;
+void plan_shards(const std::vector<HostPart>& parts, size_t g, std::vector<std::vector<Shard>>& shards) {
+    shards.assign(parts.size(), std::vector<Shard>(g, Shard{0, 0}));
+    std::vector<double> load(g, 0.0);
+    for (size_t p = 0; p < parts.size(); p++) {
+        const size_t n = parts[p].n;
+        if (n >= g * MIN_SPLIT_ITEMS) {
+            const size_t per = ((n + g - 1) / g + 31) & ~size_t(31);   // shards start on a bitmap word
+            for (size_t k = 0; k < g; k++) {
+                size_t lo = k * per < n ? k * per : n, hi = lo + per < n ? lo + per : n;
+                shards[p][k] = Shard{lo, hi};
+                load[k] += part_weight(parts[p]) * (double)(hi - lo);
+            }
+        }
+    }
+    for (size_t p = 0; p < parts.size(); p++) {
+        const size_t n = parts[p].n;
+        if (n == 0 || n >= g * MIN_SPLIT_ITEMS) continue;
+        size_t best = 0;
+        for (size_t k = 1; k < g; k++)
+            if (load[k] < load[best]) best = k;
+        shards[p][best] = Shard{0, n};
+        load[best] += part_weight(parts[p]) * (double)n;
+    }
+}
+
+struct StagedPart {   // device staging of one part's shard
+    uint8_t *pk = nullptr, *sig = nullptr, *msg = nullptr, *status = nullptr, *c = nullptr, *agg = nullptr;
+    uint32_t *offsets = nullptr, *bitmap = nullptr;
+};
+
+inline size_t part_in_bytes(const HostPart& p, size_t lo, size_t hi, size_t* pk_bytes, size_t* sig_bytes) {
+    const size_t m = hi - lo;
+    if (p.mode == PART_AGGREGATE) {
+        *pk_bytes = 32 * (size_t)(p.offsets[hi] - p.offsets[lo]);
+        *sig_bytes = 64 * m;
+    } else if (p.mode == PART_TYPED) {
+        *pk_bytes = 160 * (size_t)variant_slots(p.variant) * m;
+        *sig_bytes = 32 * m;
+    } else {
+        *pk_bytes = pk_size(p.variant) * m;
+        *sig_bytes = sig_size(p.variant) * m;
+    }
+    return *pk_bytes + *sig_bytes + 32 * m;
+}
+
+// Everything device k does for one call.  Runs on its own host thread when the context has several devices.
+int device_job(jjs_ctx* ctx, size_t k, const std::vector<HostPart>& parts, const std::vector<std::vector<Shard>>& shards) {
+    DeviceState& d = ctx->dev[k];
+    bool any = false;
+    for (size_t p = 0; p < parts.size(); p++) any = any || shards[p][k].hi > shards[p][k].lo;
+    if (!any) return JJS_SUCCESS;
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    int rc = ensure_scratch(ctx, d);
+    if (rc) return rc;
+    // staging layout
+    std::vector<StagedPart> st(parts.size());
+    std::vector<size_t> o_pk(parts.size()), o_sig(parts.size()), o_msg(parts.size()), o_st(parts.size()), o_c(parts.size()), o_agg(parts.size()),
+        o_off(parts.size()), o_bm(parts.size());
+    size_t total = 0;
+    size_t max_cnt = 0;
+    for (size_t p = 0; p < parts.size(); p++) {
+        const HostPart& P = parts[p];
+        const size_t lo = shards[p][k].lo, hi = shards[p][k].hi, m = hi - lo;
+        if (!m) continue;
+        size_t pkb, sgb;
+        part_in_bytes(P, lo, hi, &pkb, &sgb);
+        o_pk[p] = total; total += align_up(pkb, 256);
+        o_sig[p] = total; total += align_up(sgb, 256);
+        o_msg[p] = total; total += align_up(32 * m, 256);
+        o_st[p] = total; total += align_up(m, 256);
+        o_c[p] = total; total += align_up(32 * m, 256);
+        o_bm[p] = total; total += align_up(4 * ((m + 31) / 32), 256);
+        if (P.mode == PART_AGGREGATE) {
+            o_agg[p] = total; total += align_up(32 * m, 256);
+            o_off[p] = total; total += align_up(4 * (m + 1), 256);
+            size_t mc = agg_max_item_keys(P.offsets + lo, m);
+            if (mc > max_cnt) max_cnt = mc;
+            rc = ensure_agg_scratch(ctx, d, mc > AGG_KEYS_INITIAL ? mc : AGG_KEYS_INITIAL);
+            if (rc) return rc;
+        }
+    }
+    if (max_cnt) {
+        rc = ensure_tags(ctx, d, 2 + 2 * max_cnt);
+        if (rc) return rc;
+    }
+    rc = ensure_stage(ctx, d, total);
+    if (rc) return rc;
+    const bool serial = ctx->profile;   // stage timers must not overlap
+    size_t j = 0;                       // slice counter of this device: slices alternate between the compute streams / scratch halves
+    for (size_t p = 0; p < parts.size(); p++) {
+        const HostPart& P = parts[p];
+        const size_t lo = shards[p][k].lo, hi = shards[p][k].hi, m = hi - lo;
+        if (!m) continue;
+        StagedPart& S = st[p];
+        S.pk = d.stage + o_pk[p]; S.sig = d.stage + o_sig[p]; S.msg = d.stage + o_msg[p]; S.status = d.stage + o_st[p]; S.c = d.stage + o_c[p];
+        S.bitmap = reinterpret_cast<uint32_t*>(d.stage + o_bm[p]);
+        if (P.mode == PART_AGGREGATE) {
+            S.agg = d.stage + o_agg[p];
+            S.offsets = reinterpret_cast<uint32_t*>(d.stage + o_off[p]);
+            JJS_CUDA(ctx, cudaMemcpyAsync(S.offsets, P.offsets + lo, 4 * (m + 1), cudaMemcpyHostToDevice, d.copy_stream));
+        }
+        const bool want_c = P.c_out != nullptr || P.challenge_only;
+        const size_t pks = P.mode == PART_TYPED ? 160 * (size_t)variant_slots(P.variant) : pk_size(P.variant);
+        const size_t sgs = P.mode == PART_TYPED ? 32 : (P.mode == PART_AGGREGATE ? 64 : sig_size(P.variant));
+        // Pipeline slices: slice j + 1 is copied in on the copy stream while slice j is being verified (the kernels of one
+        // slice run far longer than its copy); the first slice of a device is short so that compute starts early.
+        for (size_t off = 0; off < m; j++) {
+            const size_t want = j == 0 ? SUB_CHUNK / 4 : SUB_CHUNK;
+            size_t cnt = m - off < want ? m - off : want;
+            cudaStream_t cs = serial ? d.stream : d.sub[j & 1];
+            Region R = region_half(d, j);
+            if (P.mode == PART_AGGREGATE) {
+                const uint32_t* ho = P.offsets + lo;   // host offsets of this shard
+                size_t end = agg_chunk_end(ho, off, m, want, d.agg[0].cap_keys);
+                cnt = end - off;
+                const uint32_t key0 = ho[0], key_lo = ho[off];
+                const size_t K = ho[end] - key_lo;
+                if (K) JJS_CUDA(ctx, cudaMemcpyAsync(S.pk + 32 * (size_t)(key_lo - key0), P.pk + 32 * (size_t)key_lo, 32 * K, cudaMemcpyHostToDevice, d.copy_stream));
+                JJS_CUDA(ctx, cudaMemcpyAsync(S.sig + 64 * off, P.sig + 64 * (lo + off), 64 * cnt, cudaMemcpyHostToDevice, d.copy_stream));
+                JJS_CUDA(ctx, cudaMemcpyAsync(S.msg + 32 * off, P.msg + 32 * (lo + off), 32 * cnt, cudaMemcpyHostToDevice, d.copy_stream));
+                JJS_CUDA(ctx, cudaEventRecord(d.copied, d.copy_stream));
+                JJS_CUDA(ctx, cudaStreamWaitEvent(cs, d.copied, 0));
+                rc = run_chunk_aggregate(ctx, d, R, S.pk + 32 * (size_t)(key_lo - key0), S.offsets + off, key_lo, K, S.sig + 64 * off, S.msg + 32 * off, cnt,
+                                         S.status + off, want_c ? S.c + 32 * off : nullptr, P.agg_out ? S.agg + 32 * off : nullptr, cs);
+            } else {
+                JJS_CUDA(ctx, cudaMemcpyAsync(S.pk + off * pks, P.pk + (lo + off) * pks, cnt * pks, cudaMemcpyHostToDevice, d.copy_stream));
+                JJS_CUDA(ctx, cudaMemcpyAsync(S.sig + off * sgs, P.sig + (lo + off) * sgs, cnt * sgs, cudaMemcpyHostToDevice, d.copy_stream));
+                JJS_CUDA(ctx, cudaMemcpyAsync(S.msg + off * 32, P.msg + (lo + off) * 32, cnt * 32, cudaMemcpyHostToDevice, d.copy_stream));
+                JJS_CUDA(ctx, cudaEventRecord(d.copied, d.copy_stream));
+                JJS_CUDA(ctx, cudaStreamWaitEvent(cs, d.copied, 0));
+                if (P.mode == PART_TYPED)
+                    rc = run_chunk_ext(ctx, d, R, P.variant, S.pk + off * pks, S.sig + off * 32, S.msg + off * 32, cnt, S.status + off,
+                                       want_c ? S.c + off * 32 : nullptr, cs);
+                else
+                    rc = run_chunk(ctx, d, R, P.variant, S.pk + off * pks, S.sig + off * sgs, S.msg + off * 32, cnt, S.status + off,
+                                   want_c ? S.c + off * 32 : nullptr, cs, P.challenge_only);
+            }
+            if (rc) return rc;
+            off += cnt;
+        }
+    }
+    if (!serial)
+        for (int q = 0; q < 2; q++) {
+            JJS_CUDA(ctx, cudaEventRecord(d.join[q], d.sub[q]));
+            JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.join[q], 0));
+        }
+    for (size_t p = 0; p < parts.size(); p++) {
+        const HostPart& P = parts[p];
+        const size_t lo = shards[p][k].lo, hi = shards[p][k].hi, m = hi - lo;
+        if (!m) continue;
+        const StagedPart& S = st[p];
+        if (!P.challenge_only && P.status) JJS_CUDA(ctx, cudaMemcpyAsync(P.status + lo, S.status, m, cudaMemcpyDeviceToHost, d.stream));
+        if (P.c_out) JJS_CUDA(ctx, cudaMemcpyAsync(P.c_out + lo * 32, S.c, m * 32, cudaMemcpyDeviceToHost, d.stream));
+        if (P.agg_out) JJS_CUDA(ctx, cudaMemcpyAsync(P.agg_out + lo * 32, S.agg, m * 32, cudaMemcpyDeviceToHost, d.stream));
+        if (P.bitmap) {
+            k_bitmap<<<blocks_for(m), BLOCK, 0, d.stream>>>(S.status, m, S.bitmap);
+            ctx->launches++;
+            JJS_CUDA(ctx, cudaMemcpyAsync(P.bitmap + lo / 32, S.bitmap, 4 * ((m + 31) / 32), cudaMemcpyDeviceToHost, d.stream));
+        }
+    }
+    JJS_CUDA(ctx, cudaGetLastError());
+    JJS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return JJS_SUCCESS;
+}
+
+// device_job, and on failure a drain of the device: nothing may still be reading or writing the caller's buffers when the
+// call returns
+int device_job_drained(jjs_ctx* ctx, size_t k, const std::vector<HostPart>& parts, const std::vector<std::vector<Shard>>& shards) {
+    int rc = device_job(ctx, k, parts, shards);
+    if (rc) {
         cudaSetDevice(ctx->dev[k].device);
-        cudaError_t e = cudaStreamSynchronize(ctx->dev[k].stream);
-        if (e != cudaSuccess && rc == JJS_SUCCESS) rc = fail(ctx, JJS_ERR_CUDA, "aggregate verify failed: %s", cudaGetErrorString(e));
+        cudaDeviceSynchronize();
     }
     return rc;
 }
 
-// typed inputs: points as JubJubExtended coordinates, scalars as canonical bytes; host buffers, device 0
-int run_ext(jjs_ctx* ctx, int variant, const uint8_t* pts, const uint8_t* u32, const uint8_t* msg, size_t n, uint8_t* status, uint8_t* c_out) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
-    if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
-    if (n == 0) return JJS_SUCCESS;
-    if (!pts || !u32 || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
-    const int slots = variant_slots(variant);
-    const size_t g = ctx->dev.size(), per = (n + g - 1) / g;
-    // Same structure as run_host: every device gets a contiguous shard, staged whole on the device; the shard is cut into
-    // slices (a short first one) whose H2D copies run on the copy stream while earlier slices are being verified on the
-    // two alternating compute streams / scratch halves.  Nothing is synchronised before every device has its work.
-    for (size_t k = 0; k < g; k++) {
-        size_t lo = k * per, hi = lo + per < n ? lo + per : n;
-        if (lo >= hi) break;
-        DeviceState& d = ctx->dev[k];
-        int rc = ensure_scratch(ctx, d);
-        if (rc) return rc;
-        JJS_CUDA(ctx, cudaSetDevice(d.device));
-        const size_t m = hi - lo, ptw = 160 * (size_t)slots;
-        const size_t need = m * (ptw + 32 + 32 + 32 + 1);
-        if (need > d.agg_stage_bytes) {
-            JJS_CUDA(ctx, cudaStreamSynchronize(d.stream));
-            cudaFree(d.agg_stage);
-            d.agg_stage = nullptr;
-            d.agg_stage_bytes = 0;
-            JJS_CUDA(ctx, cudaMalloc(&d.agg_stage, need));
-            d.agg_stage_bytes = need;
-        }
-        uint8_t *b_pts = d.agg_stage, *b_u = b_pts + ptw * m, *b_msg = b_u + 32 * m, *b_c = b_msg + 32 * m, *b_st = b_c + 32 * m;
-        const bool serial = ctx->profile;
-        size_t j = 0;
-        for (size_t off = 0; off < m; j++) {
-            size_t want = j == 0 ? SUB_CHUNK / 4 : SUB_CHUNK;
-            size_t cnt = m - off < want ? m - off : want;
-            JJS_CUDA(ctx, cudaMemcpyAsync(b_pts + ptw * off, pts + ptw * (lo + off), ptw * cnt, cudaMemcpyHostToDevice, d.copy_stream));
-            JJS_CUDA(ctx, cudaMemcpyAsync(b_u + 32 * off, u32 + 32 * (lo + off), 32 * cnt, cudaMemcpyHostToDevice, d.copy_stream));
-            JJS_CUDA(ctx, cudaMemcpyAsync(b_msg + 32 * off, msg + 32 * (lo + off), 32 * cnt, cudaMemcpyHostToDevice, d.copy_stream));
-            JJS_CUDA(ctx, cudaEventRecord(d.copied, d.copy_stream));
-            cudaStream_t cs = serial ? d.stream : d.sub[j & 1];
-            JJS_CUDA(ctx, cudaStreamWaitEvent(cs, d.copied, 0));
-            Region R = region_of(d, (j & 1) * SUB_ITEMS, SUB_ITEMS, (int)(j & 1));
-            WireField fmsg{b_msg + 32 * off, 32}, fu{b_u + 32 * off, 32};
-            StageTimer t0(ctx, d.device, 0, cs);
-            k_decode_ext<<<blocks_for(slots * cnt), BLOCK, 0, cs>>>(b_pts + ptw * off, slots, cnt, R.pts_u, R.pts_v, R.pflags, key_slot_mask(variant));
-            t0.stop(cs);
-            rc = enqueue_challenges(ctx, d, R, variant, cnt, fmsg, fu, cs, true);
-            if (!rc) rc = enqueue_equations(ctx, d, R, variant, cnt, fu, cs);
-            if (rc) return rc;
-            k_finalize<<<blocks_for(cnt), BLOCK, 0, cs>>>(variant, R.pflags, R.iflags, R.eqflags, R.cwords, cnt, b_st + off, c_out ? b_c + 32 * off : nullptr);
-            ctx->launches += 2;   // decode, finalize
-            off += cnt;
-        }
-        if (!serial)
-            for (int q = 0; q < 2; q++) {
-                JJS_CUDA(ctx, cudaEventRecord(d.join[q], d.sub[q]));
-                JJS_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.join[q], 0));
-            }
-        JJS_CUDA(ctx, cudaMemcpyAsync(status + lo, b_st, m, cudaMemcpyDeviceToHost, d.stream));
-        if (c_out) JJS_CUDA(ctx, cudaMemcpyAsync(c_out + 32 * lo, b_c, 32 * m, cudaMemcpyDeviceToHost, d.stream));
+int validate_part(jjs_ctx* ctx, const HostPart& P) {
+    if (P.mode == PART_WIRE || P.mode == PART_TYPED) {
+        if (P.variant < 0 || P.variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
+    } else if (P.mode != PART_AGGREGATE) {
+        return fail(ctx, JJS_ERR_ARGUMENT, "bad part kind");
     }
-    for (size_t k = 0; k < g; k++) {
-        JJS_CUDA(ctx, cudaSetDevice(ctx->dev[k].device));
-        cudaError_t e = cudaStreamSynchronize(ctx->dev[k].stream);
-        if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "typed verify failed: %s", cudaGetErrorString(e));
+    if (P.n == 0) return JJS_SUCCESS;
+    if (P.challenge_only) {
+        if (!P.pk || !P.sig || !P.msg || !P.c_out) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+        return JJS_SUCCESS;
     }
-    JJS_CUDA(ctx, cudaGetLastError());
+    if (!P.sig || !P.msg || (!P.status && !P.bitmap)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    if (P.mode == PART_AGGREGATE) {
+        if (!P.offsets) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+        for (size_t i = 0; i < P.n; i++)
+            if (P.offsets[i + 1] < P.offsets[i]) return fail(ctx, JJS_ERR_ARGUMENT, "offsets must be non-decreasing");
+        if (P.offsets[P.n] > P.offsets[0] && !P.pk) return fail(ctx, JJS_ERR_ARGUMENT, "null key buffer");
+    } else if (!P.pk) {
+        return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    }
     return JJS_SUCCESS;
+}
+
+int run_parts(jjs_ctx* ctx, const std::vector<HostPart>& parts) {
+    JJS_ENTER(ctx);
+    bool any = false;
+    for (const HostPart& P : parts) {
+        int rc = validate_part(ctx, P);
+        if (rc) return rc;
+        any = any || P.n > 0;
+    }
+    if (!any) return JJS_SUCCESS;
+    const size_t g = ctx->dev.size();
+    std::vector<std::vector<Shard>> shards;
+    plan_shards(parts, g, shards);
+    std::vector<int> rcs(g, JJS_SUCCESS);
+    if (g == 1) {
+        rcs[0] = device_job_drained(ctx, 0, parts, shards);
+    } else {
+        std::vector<std::thread> workers;
+        workers.reserve(g);
+        for (size_t k = 0; k < g; k++) workers.emplace_back([&, k] { rcs[k] = device_job_drained(ctx, k, parts, shards); });
+        for (auto& w : workers) w.join();
+    }
+    for (size_t k = 0; k < g; k++)
+        if (rcs[k]) return rcs[k];
+    return JJS_SUCCESS;
+}
+
+HostPart wire_part(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status, uint8_t* c_out, uint32_t* bitmap,
+                   bool challenge_only = false) {
+    return HostPart{PART_WIRE, variant, pk, sig, msg, nullptr, n, status, c_out, nullptr, bitmap, challenge_only};
+}
+HostPart aggregate_part(const uint8_t* pks, const uint32_t* offsets, const uint8_t* sig, const uint8_t* msg, size_t n, uint8_t* status, uint8_t* c_out,
+                        uint8_t* agg_out, uint32_t* bitmap) {
+    return HostPart{PART_AGGREGATE, VAR_SINGLE, pks, sig, msg, offsets, n, status, c_out, agg_out, bitmap, false};
 }
 
 // multisig::combine for n ragged sessions (host buffers, device 0); chunks hold at most 2^20 participants
 int run_msig(jjs_ctx* ctx, const uint8_t* pks, const uint8_t* Rs, const uint8_t* Ss, const uint8_t* zs, const uint32_t* offsets, const uint8_t* msg,
              size_t n, uint8_t* share_ok, uint8_t* status, uint32_t* bad, uint8_t* sig) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
+    JJS_ENTER(ctx);
     if (n == 0) return JJS_SUCCESS;
     if (!offsets || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     if (offsets[0] != 0) return fail(ctx, JJS_ERR_ARGUMENT, "offsets[0] must be 0");
@@ -876,6 +1216,7 @@ int run_msig(jjs_ctx* ctx, const uint8_t* pks, const uint8_t* Rs, const uint8_t*
     if (offsets[n] && (!pks || !Rs || !Ss || !zs)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     DeviceState& d = ctx->dev[0];
     int rc = ensure_scratch(ctx, d);
+    if (!rc) rc = ensure_tags(ctx, d, 3 + 4 * agg_max_item_keys(offsets, n));
     if (rc) return rc;
     JJS_CUDA(ctx, cudaSetDevice(d.device));
     Tables T = d.tables();
@@ -907,26 +1248,14 @@ int run_msig(jjs_ctx* ctx, const uint8_t* pks, const uint8_t* Rs, const uint8_t*
                o_pv = take(sizeof(fq) * 3 * K), o_pf = take(3 * K), o_d = take(32 * K), o_cd = take(32 * K), o_a = take(32 * m), o_ru = take(sizeof(fq) * m),
                o_rv = take(sizeof(fq) * m), o_sf = take(m), o_ok = take(K), o_off = take(4 * (m + 1)), o_own = take(4 * K), o_ord = take(4 * m),
                o_st = take(m), o_bad = take(4 * m), o_sig = take(64 * m);
-        if (o > d.agg_stage_bytes) {
-            cudaStreamSynchronize(d.stream);
-            cudaFree(d.agg_stage);
-            d.agg_stage = nullptr;
-            d.agg_stage_bytes = 0;
-            JJS_CUDA(ctx, cudaMalloc(&d.agg_stage, o));
-            d.agg_stage_bytes = o;
-        }
-        uint8_t* B = d.agg_stage;
+        rc = ensure_stage(ctx, d, o);
+        if (rc) return rc;
+        uint8_t* B = d.stage;
         cudaStream_t st = d.stream;
-        if (K) {
-            cudaMemcpyAsync(B + o_pk, pks + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(B + o_R, Rs + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(B + o_S, Ss + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(B + o_z, zs + 32 * k0, 32 * K, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(B + o_own, owner.data(), 4 * K, cudaMemcpyHostToDevice, st);
-        }
-        cudaMemcpyAsync(B + o_msg, msg + 32 * s0, 32 * m, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(B + o_off, rel.data(), 4 * (m + 1), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(B + o_ord, order.data(), 4 * m, cudaMemcpyHostToDevice, st);
+        cudaError_t ce = cudaSuccess;
+        auto up = [&](size_t at, const void* src, size_t bytes) { if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(B + at, src, bytes, cudaMemcpyHostToDevice, st); };
+        up(o_pk, pks + 32 * k0, 32 * K); up(o_R, Rs + 32 * k0, 32 * K); up(o_S, Ss + 32 * k0, 32 * K); up(o_z, zs + 32 * k0, 32 * K);
+        up(o_own, owner.data(), 4 * K); up(o_msg, msg + 32 * s0, 32 * m); up(o_off, rel.data(), 4 * (m + 1)); up(o_ord, order.data(), 4 * m);
         MsigBuffers b;
         b.pu = reinterpret_cast<fq*>(B + o_pu); b.pv = reinterpret_cast<fq*>(B + o_pv); b.pf = B + o_pf;
         b.d_words = reinterpret_cast<uint32_t*>(B + o_d); b.cd_words = reinterpret_cast<uint32_t*>(B + o_cd); b.a_words = reinterpret_cast<uint32_t*>(B + o_a);
@@ -936,15 +1265,17 @@ int run_msig(jjs_ctx* ctx, const uint8_t* pks, const uint8_t* Rs, const uint8_t*
         f.f[0] = WireField{B + o_pk, 32}; f.f[1] = WireField{B + o_R, 32}; f.f[2] = WireField{B + o_S, 32}; f.f[3] = WireField{nullptr, 0};
         WireField fmsg{B + o_msg, 32}, fz{B + o_z, 32};
         if (K) k_decode<<<blocks_for(3 * K), BLOCK, 0, st>>>(f, 3, 0, K, b.pu, b.pv, b.pf, T, 0u);
-        k_msig_session<<<blocks_for(m), BLOCK, 0, st>>>(b, K, m, fmsg, fz, d.tab, TAB_THREADS);
+        k_msig_session<<<blocks_for(m), BLOCK, 0, st>>>(b, K, m, fmsg, fz, d.tab, TAB_THREADS, T);
         if (K) k_msig_share<<<blocks_for(K), BLOCK, 0, st>>>(b, K, fz, d.tab, TAB_THREADS, T);
         k_msig_finalize<<<blocks_for(m), BLOCK, 0, st>>>(b, m, fz, B + o_st, reinterpret_cast<uint32_t*>(B + o_bad), B + o_sig);
         ctx->launches += 4;
-        cudaMemcpyAsync(status + s0, B + o_st, m, cudaMemcpyDeviceToHost, st);
-        if (bad) cudaMemcpyAsync(bad + s0, B + o_bad, 4 * m, cudaMemcpyDeviceToHost, st);
-        if (sig) cudaMemcpyAsync(sig + 64 * s0, B + o_sig, 64 * m, cudaMemcpyDeviceToHost, st);
-        if (share_ok && K) cudaMemcpyAsync(share_ok + k0, B + o_ok, K, cudaMemcpyDeviceToHost, st);
-        cudaError_t e = cudaStreamSynchronize(st);
+        auto down = [&](void* dst, size_t at, size_t bytes) { if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(dst, B + at, bytes, cudaMemcpyDeviceToHost, st); };
+        down(status + s0, o_st, m);
+        if (bad) down(bad + s0, o_bad, 4 * m);
+        if (sig) down(sig + 64 * s0, o_sig, 64 * m);
+        if (share_ok) down(share_ok + k0, o_ok, K);
+        cudaError_t e = cudaStreamSynchronize(st);   // also the drain of the error path: the host vectors above are reused by the next chunk
+        if (ce != cudaSuccess) e = ce;
         if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "multisig combine failed: %s", cudaGetErrorString(e));
         s0 = s1;
     }
@@ -953,37 +1284,38 @@ int run_msig(jjs_ctx* ctx, const uint8_t* pks, const uint8_t* Rs, const uint8_t*
 
 int run_sign(jjs_ctx* ctx, int variant, const uint8_t* sk, const uint8_t* rnd, const uint8_t* gsc, const uint8_t* msg, size_t n, uint8_t* pk_out,
              uint8_t* sig_out) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
+    JJS_ENTER(ctx);
     if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
     if (n == 0) return JJS_SUCCESS;
     if (!sk || !rnd || !msg || !pk_out || !sig_out || (variant == VAR_VARGEN && !gsc)) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     DeviceState& d = ctx->dev[0];
     JJS_CUDA(ctx, cudaSetDevice(d.device));
     const size_t pks = pk_size(variant), sgs = sig_size(variant);
-    uint8_t* buf = nullptr;
     const size_t chunk = n < CHUNK_ITEMS ? n : CHUNK_ITEMS;
-    JJS_CUDA(ctx, cudaMalloc(&buf, chunk * (4 * 32 + pks + sgs)));
+    int rc = ensure_stage(ctx, d, chunk * (4 * 32 + pks + sgs));
+    if (rc) return rc;
+    uint8_t* buf = d.stage;
     uint8_t *d_sk = buf, *d_rnd = buf + 32 * chunk, *d_g = buf + 64 * chunk, *d_msg = buf + 96 * chunk, *d_pk = buf + 128 * chunk,
             *d_sig = d_pk + pks * chunk;
-    int rc = JJS_SUCCESS;
-    for (size_t off = 0; off < n && rc == JJS_SUCCESS; off += chunk) {
+    for (size_t off = 0; off < n; off += chunk) {
         size_t m = n - off < chunk ? n - off : chunk;
-        cudaMemcpyAsync(d_sk, sk + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
-        cudaMemcpyAsync(d_rnd, rnd + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
-        if (variant == VAR_VARGEN) cudaMemcpyAsync(d_g, gsc + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
-        cudaMemcpyAsync(d_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
-        if (variant == VAR_SINGLE) k_sign<VAR_SINGLE><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
-        else if (variant == VAR_DOUBLE) k_sign<VAR_DOUBLE><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
-        else k_sign<VAR_VARGEN><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
-        ctx->launches++;
-        cudaMemcpyAsync(pk_out + pks * off, d_pk, pks * m, cudaMemcpyDeviceToHost, d.stream);
-        cudaMemcpyAsync(sig_out + sgs * off, d_sig, sgs * m, cudaMemcpyDeviceToHost, d.stream);
+        cudaError_t ce = cudaMemcpyAsync(d_sk, sk + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_rnd, rnd + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        if (ce == cudaSuccess && variant == VAR_VARGEN) ce = cudaMemcpyAsync(d_g, gsc + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_msg, msg + 32 * off, 32 * m, cudaMemcpyHostToDevice, d.stream);
+        if (ce == cudaSuccess) {
+            if (variant == VAR_SINGLE) k_sign<VAR_SINGLE><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
+            else if (variant == VAR_DOUBLE) k_sign<VAR_DOUBLE><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
+            else k_sign<VAR_VARGEN><<<blocks_for(m), BLOCK, 0, d.stream>>>(d_sk, d_rnd, d_g, d_msg, m, d_pk, d_sig, d.tables());
+            ctx->launches++;
+            ce = cudaMemcpyAsync(pk_out + pks * off, d_pk, pks * m, cudaMemcpyDeviceToHost, d.stream);
+        }
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(sig_out + sgs * off, d_sig, sgs * m, cudaMemcpyDeviceToHost, d.stream);
         cudaError_t e = cudaStreamSynchronize(d.stream);
-        if (e != cudaSuccess) rc = fail(ctx, JJS_ERR_CUDA, "sign batch failed: %s", cudaGetErrorString(e));
+        if (ce != cudaSuccess) e = ce;
+        if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "sign batch failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(buf);
-    return rc;
+    return JJS_SUCCESS;
 }
 
 int init_device(jjs_ctx* ctx, DeviceState& d) {
@@ -1011,16 +1343,20 @@ int init_device(jjs_ctx* ctx, DeviceState& d) {
     ctx->launches += 2;
     JJS_CUDA(ctx, cudaGetLastError());
     JJS_CUDA(ctx, cudaStreamSynchronize(d.stream));
-    return JJS_SUCCESS;
+    return ensure_tags(ctx, d, 1023);
 }
 
 void free_device(DeviceState& d) {
     if (d.device < 0) return;
     cudaSetDevice(d.device);
-    cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn);
-    cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords); cudaFree(d.rlist); cudaFree(d.rcount); cudaFree(d.eqlist);
-    cudaFree(d.s_pk); cudaFree(d.s_sig); cudaFree(d.s_msg); cudaFree(d.s_status); cudaFree(d.s_c); cudaFree(d.s_bitmap);
-    cudaFree(d.keys_u); cudaFree(d.keys_v); cudaFree(d.kflags); cudaFree(d.kcoef); cudaFree(d.agg_stage); cudaFree(d.d_order);
+    cudaDeviceSynchronize();
+    cudaFree(d.root_tables); cudaFree(d.dlog_hash); cudaFree(d.fb_g); cudaFree(d.fb_gn); cudaFree(d.safe_tags);
+    cudaFree(d.pts_u); cudaFree(d.pts_v); cudaFree(d.tab); cudaFree(d.eqtab); cudaFree(d.pflags); cudaFree(d.iflags); cudaFree(d.eqflags); cudaFree(d.cwords);
+    cudaFree(d.rlist); cudaFree(d.rcount); cudaFree(d.eqlist); cudaFree(d.stage);
+    for (int h = 0; h < 2; h++) {
+        AggScratch& a = d.agg[h];
+        cudaFree(a.keys_u); cudaFree(a.keys_v); cudaFree(a.kflags); cudaFree(a.kcoef); cudaFree(a.kmap); cudaFree(a.kitem); cudaFree(a.order); cudaFree(a.sort);
+    }
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.copied) cudaEventDestroy(d.copied);
@@ -1033,13 +1369,38 @@ void free_device(DeviceState& d) {
 
 int device_entry(jjs_ctx* ctx, int variant, int device_index, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg, size_t n,
                  uint8_t* status, uint8_t* c_out, void* stream) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
+    JJS_ENTER(ctx);
     if (device_index < 0 || (size_t)device_index >= ctx->dev.size()) return fail(ctx, JJS_ERR_ARGUMENT, "device_index out of range");
     if (n == 0) return JJS_SUCCESS;
     if (!pk || !sig || !msg || !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     DeviceState& d = ctx->dev[device_index];
     return run_device(ctx, d, variant, pk, sig, msg, n, status, c_out, (cudaStream_t)stream);
+}
+
+// small synchronous utilities on device 0: copy in, one kernel, copy out
+template <typename Launch>
+int run_small(jjs_ctx* ctx, const char* what, size_t in_bytes, size_t out_bytes, const void* const* srcs, const size_t* src_bytes, int n_src, void* dst,
+              Launch launch) {
+    DeviceState& d = ctx->dev[0];
+    JJS_CUDA(ctx, cudaSetDevice(d.device));
+    int rc = ensure_stage(ctx, d, align_up(in_bytes, 256) + out_bytes);
+    if (rc) return rc;
+    cudaError_t ce = cudaSuccess;
+    size_t at = 0;
+    for (int i = 0; i < n_src && ce == cudaSuccess; i++) {
+        if (src_bytes[i]) ce = cudaMemcpyAsync(d.stage + at, srcs[i], src_bytes[i], cudaMemcpyHostToDevice, d.stream);
+        at += src_bytes[i];
+    }
+    uint8_t* d_out = d.stage + align_up(in_bytes, 256);
+    if (ce == cudaSuccess) {
+        launch(d, d.stage, d_out);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, d_out, out_bytes, cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    if (ce != cudaSuccess) e = ce;
+    if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    return JJS_SUCCESS;
 }
 
 }  // namespace
@@ -1054,32 +1415,22 @@ JJS_API int jjs_init(const int* devices, int n_devices, jjs_ctx** out) {
     jjs_ctx* ctx = new (std::nothrow) jjs_ctx();
     if (!ctx) return JJS_ERR_NOMEM;
     ctx->err[0] = 0;
-    ctx->launches = 0;
-    ctx->profile = false;
+    *out = ctx;   // on failure the context is returned unusable, only so that the caller can read the reason: no CPU fallback
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count < 1) {
-        // no CPU fallback: the context is returned unusable only so the caller can read the reason
-        fail(ctx, JJS_ERR_CUDA, "no CUDA device available: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-        *out = ctx;
-        return JJS_ERR_CUDA;
-    }
+    if (e != cudaSuccess || count < 1)
+        return fail(ctx, JJS_ERR_CUDA, "no CUDA device available: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     ctx->dev.resize(n_devices);
     for (int i = 0; i < n_devices; i++) {
-        ctx->dev[i].device = devices ? devices[i] : i;
-        if (ctx->dev[i].device < 0 || ctx->dev[i].device >= count) {
-            fail(ctx, JJS_ERR_ARGUMENT, "device ordinal %d not present (%d devices)", ctx->dev[i].device, count);
-            ctx->dev[i].device = -1;
-            *out = ctx;
-            return JJS_ERR_ARGUMENT;
-        }
+        int ord = devices ? devices[i] : i;
+        if (ord < 0 || ord >= count) return fail(ctx, JJS_ERR_ARGUMENT, "device ordinal %d not present (%d devices)", ord, count);
+        for (int k = 0; k < i; k++)
+            if (ctx->dev[k].device == ord) return fail(ctx, JJS_ERR_ARGUMENT, "device ordinal %d listed twice", ord);
+        ctx->dev[i].device = ord;
         int rc = init_device(ctx, ctx->dev[i]);
-        if (rc) {
-            *out = ctx;
-            return rc;
-        }
+        if (rc) return rc;
     }
-    *out = ctx;
+    ctx->ready = true;
     return JJS_SUCCESS;
 }
 
@@ -1090,20 +1441,58 @@ JJS_API void jjs_destroy(jjs_ctx* ctx) {
 }
 
 JJS_API const char* jjs_last_error(const jjs_ctx* ctx) { return ctx ? ctx->err : "null context"; }
-JJS_API int jjs_device_count(const jjs_ctx* ctx) { return ctx ? (int)ctx->dev.size() : 0; }
-JJS_API uint64_t jjs_launch_count(const jjs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+JJS_API int jjs_device_count(const jjs_ctx* ctx) { return ctx && ctx->ready ? (int)ctx->dev.size() : 0; }
+JJS_API uint64_t jjs_launch_count(const jjs_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 JJS_API int jjs_verify_single(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint8_t* status,
                               uint8_t* c32_or_null) {
-    return run_host(ctx, VAR_SINGLE, pk32, sig64, msg32, n, status, c32_or_null);
+    return run_parts(ctx, {wire_part(VAR_SINGLE, pk32, sig64, msg32, n, status, c32_or_null, nullptr)});
+}
+JJS_API int jjs_verify_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n, uint8_t* status,
+                              uint8_t* c32_or_null) {
+    return run_parts(ctx, {wire_part(VAR_DOUBLE, pk64, sig96, msg32, n, status, c32_or_null, nullptr)});
+}
+JJS_API int jjs_verify_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint8_t* status,
+                              uint8_t* c32_or_null) {
+    return run_parts(ctx, {wire_part(VAR_VARGEN, pk64, sig64, msg32, n, status, c32_or_null, nullptr)});
+}
+JJS_API int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* offsets, const uint8_t* sig64, const uint8_t* msg32, size_t n,
+                                 uint8_t* status, uint8_t* c32_or_null, uint8_t* aggpk32_or_null) {
+    if (ctx && ctx->ready && n && !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_parts(ctx, {aggregate_part(pks32, offsets, sig64, msg32, n, status, c32_or_null, aggpk32_or_null, nullptr)});
 }
 JJS_API int jjs_verify_batch(jjs_ctx* ctx, const uint8_t* pk32, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint32_t* accept_bitmap) {
-    if (ctx && n && !accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
-    return run_host(ctx, VAR_SINGLE, pk32, sig64, msg32, n, nullptr, nullptr, false, accept_bitmap);
+    if (ctx && ctx->ready && n && !accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_parts(ctx, {wire_part(VAR_SINGLE, pk32, sig64, msg32, n, nullptr, nullptr, accept_bitmap)});
+}
+JJS_API int jjs_verify_batch_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n, uint32_t* accept_bitmap) {
+    if (ctx && ctx->ready && n && !accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_parts(ctx, {wire_part(VAR_DOUBLE, pk64, sig96, msg32, n, nullptr, nullptr, accept_bitmap)});
+}
+JJS_API int jjs_verify_batch_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint32_t* accept_bitmap) {
+    if (ctx && ctx->ready && n && !accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_parts(ctx, {wire_part(VAR_VARGEN, pk64, sig64, msg32, n, nullptr, nullptr, accept_bitmap)});
+}
+JJS_API int jjs_verify_batch_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* offsets, const uint8_t* sig64, const uint8_t* msg32, size_t n,
+                                       uint32_t* accept_bitmap) {
+    if (ctx && ctx->ready && n && !accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_parts(ctx, {aggregate_part(pks32, offsets, sig64, msg32, n, nullptr, nullptr, nullptr, accept_bitmap)});
+}
+JJS_API int jjs_verify_mixed(jjs_ctx* ctx, const jjs_part* parts, size_t n_parts) {
+    JJS_ENTER(ctx);
+    if (n_parts && !parts) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    std::vector<HostPart> hp;
+    hp.reserve(n_parts);
+    for (size_t i = 0; i < n_parts; i++) {
+        const jjs_part& p = parts[i];
+        if (p.kind < JJS_KIND_SINGLE || p.kind > JJS_KIND_AGGREGATE) return fail(ctx, JJS_ERR_ARGUMENT, "part %zu: bad kind", i);
+        if (p.kind == JJS_KIND_AGGREGATE) hp.push_back(aggregate_part(p.pk, p.offsets, p.sig, p.msg32, p.n, p.status, p.c32, p.aggpk32, p.accept_bitmap));
+        else hp.push_back(wire_part(p.kind, p.pk, p.sig, p.msg32, p.n, p.status, p.c32, p.accept_bitmap));
+    }
+    return run_parts(ctx, hp);
 }
 JJS_API int jjs_status_bitmap_device(jjs_ctx* ctx, int device_index, const uint8_t* d_status, size_t n, uint32_t* d_accept_bitmap, void* cuda_stream) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
+    JJS_ENTER(ctx);
     if (device_index < 0 || (size_t)device_index >= ctx->dev.size()) return fail(ctx, JJS_ERR_ARGUMENT, "device_index out of range");
     if (n == 0) return JJS_SUCCESS;
     if (!d_status || !d_accept_bitmap) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
@@ -1112,18 +1501,6 @@ JJS_API int jjs_status_bitmap_device(jjs_ctx* ctx, int device_index, const uint8
     ctx->launches++;
     JJS_CUDA(ctx, cudaGetLastError());
     return JJS_SUCCESS;
-}
-JJS_API int jjs_verify_double(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig96, const uint8_t* msg32, size_t n, uint8_t* status,
-                              uint8_t* c32_or_null) {
-    return run_host(ctx, VAR_DOUBLE, pk64, sig96, msg32, n, status, c32_or_null);
-}
-JJS_API int jjs_verify_vargen(jjs_ctx* ctx, const uint8_t* pk64, const uint8_t* sig64, const uint8_t* msg32, size_t n, uint8_t* status,
-                              uint8_t* c32_or_null) {
-    return run_host(ctx, VAR_VARGEN, pk64, sig64, msg32, n, status, c32_or_null);
-}
-JJS_API int jjs_verify_aggregate(jjs_ctx* ctx, const uint8_t* pks32, const uint32_t* offsets, const uint8_t* sig64, const uint8_t* msg32, size_t n,
-                                 uint8_t* status, uint8_t* c32_or_null, uint8_t* aggpk32_or_null) {
-    return run_aggregate(ctx, pks32, offsets, sig64, msg32, n, status, c32_or_null, aggpk32_or_null);
 }
 JJS_API int jjs_verify_single_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pk32, const uint8_t* d_sig64, const uint8_t* d_msg32,
                                      size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {
@@ -1137,93 +1514,93 @@ JJS_API int jjs_verify_vargen_device(jjs_ctx* ctx, int device_index, const uint8
                                      size_t n, uint8_t* d_status, uint8_t* d_c32_or_null, void* cuda_stream) {
     return device_entry(ctx, VAR_VARGEN, device_index, d_pk64, d_sig64, d_msg32, n, d_status, d_c32_or_null, cuda_stream);
 }
-JJS_API int jjs_subgroup_check(jjs_ctx* ctx, const uint8_t* points32, size_t n, int method, uint8_t* out) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
-    if (method < 0 || method > 1) return fail(ctx, JJS_ERR_ARGUMENT, "bad method");
-    if (n == 0) return JJS_SUCCESS;
-    if (!points32 || !out) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
-    DeviceState& d = ctx->dev[0];
-    int rc = ensure_scratch(ctx, d);
-    if (rc) return rc;
-    JJS_CUDA(ctx, cudaSetDevice(d.device));
-    uint8_t *d_in = nullptr, *d_out = nullptr;
-    JJS_CUDA(ctx, cudaMalloc(&d_in, 32 * n));
-    JJS_CUDA(ctx, cudaMalloc(&d_out, n));
-    cudaMemcpyAsync(d_in, points32, 32 * n, cudaMemcpyHostToDevice, d.stream);
-    for (size_t first = 0; first < n; first += TAB_THREADS) {
-        size_t cnt = n - first < TAB_THREADS ? n - first : TAB_THREADS;
-        k_subgroup_check<<<blocks_for(cnt), BLOCK, 0, d.stream>>>(WireField{d_in, 32}, first, cnt, method, d_out, d.tab, TAB_THREADS, d.tables());
-        ctx->launches++;
-    }
-    cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, d.stream);
-    cudaError_t e = cudaStreamSynchronize(d.stream);
-    cudaFree(d_in);
-    cudaFree(d_out);
-    if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "subgroup check failed: %s", cudaGetErrorString(e));
-    return JJS_SUCCESS;
-}
 JJS_API int jjs_verify_aggregate_device(jjs_ctx* ctx, int device_index, const uint8_t* d_pks32, const uint32_t* d_offsets, const uint32_t* h_offsets,
                                         const uint8_t* d_sig64, const uint8_t* d_msg32, size_t n, uint8_t* d_status, uint8_t* d_c32_or_null,
                                         uint8_t* d_aggpk32_or_null, void* cuda_stream) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
+    JJS_ENTER(ctx);
     if (device_index < 0 || (size_t)device_index >= ctx->dev.size()) return fail(ctx, JJS_ERR_ARGUMENT, "device_index out of range");
     if (n == 0) return JJS_SUCCESS;
     if (!d_offsets || !h_offsets || !d_sig64 || !d_msg32 || !d_status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    for (size_t i = 0; i < n; i++)
+        if (h_offsets[i + 1] < h_offsets[i]) return fail(ctx, JJS_ERR_ARGUMENT, "offsets must be non-decreasing");
+    if (h_offsets[n] > h_offsets[0] && !d_pks32) return fail(ctx, JJS_ERR_ARGUMENT, "null key buffer");
     return run_aggregate_device(ctx, ctx->dev[device_index], d_pks32, d_offsets, h_offsets, d_sig64, d_msg32, n, d_status, d_c32_or_null,
                                 d_aggpk32_or_null, (cudaStream_t)cuda_stream);
 }
+JJS_API int jjs_verify_ext(jjs_ctx* ctx, int variant, const uint8_t* points_ext160, const uint8_t* u32, const uint8_t* msg32, size_t n,
+                           uint8_t* status, uint8_t* c32_or_null) {
+    if (ctx && ctx->ready && n && !status) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    return run_parts(ctx, {HostPart{PART_TYPED, variant, points_ext160, u32, msg32, nullptr, n, status, c32_or_null, nullptr, nullptr, false}});
+}
+JJS_API int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32, size_t n, uint8_t* c32) {
+    return run_parts(ctx, {wire_part(variant, pk, sig, msg32, n, nullptr, c32, nullptr, true)});
+}
+JJS_API int jjs_subgroup_check(jjs_ctx* ctx, const uint8_t* points32, size_t n, int method, uint8_t* out) {
+    JJS_ENTER(ctx);
+    if (method < 0 || method > 1) return fail(ctx, JJS_ERR_ARGUMENT, "bad method");
+    if (n == 0) return JJS_SUCCESS;
+    if (!points32 || !out) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    int rc = ensure_scratch(ctx, ctx->dev[0]);
+    if (rc) return rc;
+    const void* srcs[1] = {points32};
+    const size_t bytes[1] = {32 * n};
+    return run_small(ctx, "subgroup check", 32 * n, n, srcs, bytes, 1, out, [&](DeviceState& d, uint8_t* in, uint8_t* o) {
+        for (size_t first = 0; first < n; first += TAB_THREADS) {
+            size_t cnt = n - first < TAB_THREADS ? n - first : TAB_THREADS;
+            k_subgroup_check<<<blocks_for(cnt), BLOCK, 0, d.stream>>>(WireField{in, 32}, first, cnt, method, o, d.tab, TAB_THREADS, d.tables());
+            ctx->launches++;
+        }
+    });
+}
 JJS_API int jjs_sign_aggregate_batch(jjs_ctx* ctx, const uint8_t* sk32, const uint32_t* offsets, const uint8_t* rnd32, const uint8_t* msg32, size_t n,
                                      uint8_t* pks32_out, uint8_t* sig64_out) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
+    JJS_ENTER(ctx);
     if (n == 0) return JJS_SUCCESS;
     if (!sk32 || !offsets || !rnd32 || !msg32 || !pks32_out || !sig64_out) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
     if (offsets[0] != 0) return fail(ctx, JJS_ERR_ARGUMENT, "offsets[0] must be 0");
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, JJS_ERR_ARGUMENT, "offsets must be non-decreasing");
+    const size_t K = offsets[n];
+    const size_t off_bytes = align_up(4 * (n + 1), 32);
+    const void* srcs[4] = {sk32, offsets, rnd32, msg32};
+    const size_t bytes[4] = {32 * K, off_bytes, 32 * n, 32 * n};   // the offsets slot is padded; only 4 (n + 1) bytes are meaningful
+    // the padded tail of the offsets copy must stay inside the caller's array: copy exactly, pad on the device side
+    const size_t exact[4] = {32 * K, 4 * (n + 1), 32 * n, 32 * n};
     DeviceState& d = ctx->dev[0];
     JJS_CUDA(ctx, cudaSetDevice(d.device));
-    const size_t K = offsets[n];
-    uint8_t* b = nullptr;
-    size_t o_off = 32 * K, o_rnd = o_off + ((4 * (n + 1) + 31) / 32) * 32, o_msg = o_rnd + 32 * n, o_pks = o_msg + 32 * n, o_sig = o_pks + 32 * K,
-           total = o_sig + 64 * n;
-    JJS_CUDA(ctx, cudaMalloc(&b, total));
-    cudaMemcpyAsync(b, sk32, 32 * K, cudaMemcpyHostToDevice, d.stream);
-    cudaMemcpyAsync(b + o_off, offsets, 4 * (n + 1), cudaMemcpyHostToDevice, d.stream);
-    cudaMemcpyAsync(b + o_rnd, rnd32, 32 * n, cudaMemcpyHostToDevice, d.stream);
-    cudaMemcpyAsync(b + o_msg, msg32, 32 * n, cudaMemcpyHostToDevice, d.stream);
-    k_sign_aggregate<<<blocks_for(n), BLOCK, 0, d.stream>>>(b, reinterpret_cast<uint32_t*>(b + o_off), b + o_rnd, b + o_msg, n, b + o_pks, b + o_sig,
-                                                          d.tables());
-    ctx->launches++;
-    cudaMemcpyAsync(pks32_out, b + o_pks, 32 * K, cudaMemcpyDeviceToHost, d.stream);
-    cudaMemcpyAsync(sig64_out, b + o_sig, 64 * n, cudaMemcpyDeviceToHost, d.stream);
+    const size_t in_bytes = bytes[0] + bytes[1] + bytes[2] + bytes[3];
+    int rc = ensure_stage(ctx, d, align_up(in_bytes, 256) + 32 * K + 64 * n);
+    if (rc) return rc;
+    cudaError_t ce = cudaSuccess;
+    size_t at = 0;
+    for (int i = 0; i < 4 && ce == cudaSuccess; i++) {
+        if (exact[i]) ce = cudaMemcpyAsync(d.stage + at, srcs[i], exact[i], cudaMemcpyHostToDevice, d.stream);
+        at += bytes[i];
+    }
+    uint8_t *b = d.stage, *o_pks = d.stage + align_up(in_bytes, 256), *o_sig = o_pks + 32 * K;
+    if (ce == cudaSuccess) {
+        k_sign_aggregate<<<blocks_for(n), BLOCK, 0, d.stream>>>(b, reinterpret_cast<uint32_t*>(b + bytes[0]), b + bytes[0] + bytes[1],
+                                                              b + bytes[0] + bytes[1] + bytes[2], n, o_pks, o_sig, d.tables());
+        ctx->launches++;
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess && K) ce = cudaMemcpyAsync(pks32_out, o_pks, 32 * K, cudaMemcpyDeviceToHost, d.stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(sig64_out, o_sig, 64 * n, cudaMemcpyDeviceToHost, d.stream);
     cudaError_t e = cudaStreamSynchronize(d.stream);
-    cudaFree(b);
+    if (ce != cudaSuccess) e = ce;
     if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "sign aggregate batch failed: %s", cudaGetErrorString(e));
     return JJS_SUCCESS;
 }
-JJS_API int jjs_verify_ext(jjs_ctx* ctx, int variant, const uint8_t* points_ext160, const uint8_t* u32, const uint8_t* msg32, size_t n,
-                           uint8_t* status, uint8_t* c32_or_null) {
-    return run_ext(ctx, variant, points_ext160, u32, msg32, n, status, c32_or_null);
-}
 JJS_API int jjs_points_to_ext(jjs_ctx* ctx, const uint8_t* points32, const uint8_t* z_mont32, size_t n, uint8_t* out160) {
-    if (!ctx) return JJS_ERR_ARGUMENT;
-    ctx->err[0] = 0;
+    JJS_ENTER(ctx);
     if (n == 0) return JJS_SUCCESS;
     if (!points32 || !z_mont32 || !out160) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
-    DeviceState& d = ctx->dev[0];
-    JJS_CUDA(ctx, cudaSetDevice(d.device));
-    uint8_t* b = nullptr;
-    JJS_CUDA(ctx, cudaMalloc(&b, n * (32 + 32 + 160)));
-    cudaMemcpyAsync(b, points32, 32 * n, cudaMemcpyHostToDevice, d.stream);
-    cudaMemcpyAsync(b + 32 * n, z_mont32, 32 * n, cudaMemcpyHostToDevice, d.stream);
-    k_points_to_ext<<<blocks_for(n), BLOCK, 0, d.stream>>>(b, b + 32 * n, n, b + 64 * n, d.tables());
-    ctx->launches++;
-    cudaMemcpyAsync(out160, b + 64 * n, 160 * n, cudaMemcpyDeviceToHost, d.stream);
-    cudaError_t e = cudaStreamSynchronize(d.stream);
-    cudaFree(b);
-    if (e != cudaSuccess) return fail(ctx, JJS_ERR_CUDA, "points_to_ext failed: %s", cudaGetErrorString(e));
-    return JJS_SUCCESS;
+    const void* srcs[2] = {points32, z_mont32};
+    const size_t bytes[2] = {32 * n, 32 * n};
+    return run_small(ctx, "points_to_ext", 64 * n, 160 * n, srcs, bytes, 2, out160, [&](DeviceState& d, uint8_t* in, uint8_t* o) {
+        k_points_to_ext<<<blocks_for(n), BLOCK, 0, d.stream>>>(in, in + 32 * n, n, o, d.tables());
+        ctx->launches++;
+    });
 }
 JJS_API int jjs_multisig_combine(jjs_ctx* ctx, const uint8_t* pks32, const uint8_t* R32, const uint8_t* S32, const uint8_t* z32, const uint32_t* offsets,
                                  const uint8_t* msg32, size_t n, uint8_t* share_ok_or_null, uint8_t* status, uint32_t* bad_index_or_null,
@@ -1236,7 +1613,13 @@ JJS_API void jjs_profile_enable(jjs_ctx* ctx, int on) {
 JJS_API int jjs_profile_collect(jjs_ctx* ctx, double* stage_ms, uint64_t* stage_count) {
     if (!ctx || !stage_ms || !stage_count) return JJS_ERR_ARGUMENT;
     for (int i = 0; i < JJS_N_STAGES; i++) { stage_ms[i] = 0; stage_count[i] = 0; }
-    for (auto& r : ctx->records) {
+    std::vector<StageRecord> records;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        records.swap(ctx->records);
+    }
+    int rc = JJS_SUCCESS;
+    for (auto& r : records) {
         cudaSetDevice(r.device);
         float ms = 0;
         cudaError_t e = cudaEventSynchronize(r.e1);
@@ -1244,22 +1627,17 @@ JJS_API int jjs_profile_collect(jjs_ctx* ctx, double* stage_ms, uint64_t* stage_
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
         if (e != cudaSuccess) {
-            ctx->records.clear();
-            return fail(ctx, JJS_ERR_CUDA, "profile collect: %s", cudaGetErrorString(e));
+            if (rc == JJS_SUCCESS) rc = fail(ctx, JJS_ERR_CUDA, "profile collect: %s", cudaGetErrorString(e));
+            continue;
         }
         stage_ms[r.stage] += ms;
         stage_count[r.stage]++;
     }
-    ctx->records.clear();
-    return JJS_SUCCESS;
+    return rc;
 }
 JJS_API int jjs_sign_batch(jjs_ctx* ctx, int variant, const uint8_t* sk32, const uint8_t* rnd32, const uint8_t* gen_scalar32_or_null,
                            const uint8_t* msg32, size_t n, uint8_t* pk_out, uint8_t* sig_out) {
     return run_sign(ctx, variant, sk32, rnd32, gen_scalar32_or_null, msg32, n, pk_out, sig_out);
-}
-JJS_API int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t* msg32, size_t n, uint8_t* c32) {
-    if (variant < 0 || variant > 2) return fail(ctx, JJS_ERR_ARGUMENT, "bad variant");
-    return run_host(ctx, variant, pk, sig, msg32, n, nullptr, c32, true);
 }
 
 }  // extern "C"

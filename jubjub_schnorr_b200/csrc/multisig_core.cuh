@@ -14,7 +14,6 @@ namespace jjs {
 
 constexpr uint8_t SF_DECODED = 1;      // every field of the session decodes
 constexpr uint8_t SF_NONEMPTY = 2;     // at least one participant (else InvalidMultisigTranscript)
-constexpr int MSIG_MAX_SIGNERS = 31;   // 3 + 4 n absorbed elements must stay within the precomputed SAFE tags
 
 JJS_HD void fr_add(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // a, b < r
     uint32_t s[8], t[8], ord[8];
@@ -29,7 +28,7 @@ JJS_HD void fr_add(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // a,
 // decoded points of the whole batch: index j (pk), K + j (R), 2K + j (S)
 JJS_HD void stage_msig_session(const fq* pu, const fq* pv, const uint8_t* pf, size_t K, uint32_t lo, uint32_t hi, const WireField& msg,
                                const WireField& zf, size_t session, uint32_t* d_words, uint32_t* cd_words, uint32_t* a_words, fq* rsa_u, fq* rsa_v,
-                               uint8_t* sflags, fq* tabA, size_t stride) {
+                               uint8_t* sflags, fq* tabA, size_t stride, const fq* tags) {
     uint32_t w[8];
     fq m;
     wire_load(w, msg, session);
@@ -39,14 +38,14 @@ JJS_HD void stage_msig_session(const fq* pu, const fq* pv, const uint8_t* pf, si
         wire_load(w, zf, j);
         decoded = decoded && fr_wire_is_canonical(w);
     }
-    uint8_t fl = (decoded ? SF_DECODED : 0) | ((hi > lo && hi - lo <= (uint32_t)MSIG_MAX_SIGNERS) ? SF_NONEMPTY : 0);
+    uint8_t fl = (decoded ? SF_DECODED : 0) | (hi > lo ? SF_NONEMPTY : 0);
     sflags[session] = fl;
     if (fl != (SF_DECODED | SF_NONEMPTY)) return;
     // aggregate key
     ext acc;
     ext_identity(acc);
 #pragma unroll 1
-    for (uint32_t j = lo; j < hi; j += AGG_GROUP) aggregate_group(acc, pu, pv, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tabA, stride);
+    for (uint32_t j = lo; j < hi; j += AGG_GROUP) aggregate_group(acc, pu, pv, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tabA, stride, tags);
     fq zi, au, av;
     fq_inv(zi, acc.Z);
     fq_mul(au, acc.X, zi);
@@ -55,7 +54,7 @@ JJS_HD void stage_msig_session(const fq* pu, const fq* pv, const uint8_t* pf, si
     uint32_t a[8];
     {
         Sponge sp;
-        sponge_start(sp, (int)(3 + 4 * (hi - lo)));
+        sponge_start_tag(sp, tags[3 + 4 * (size_t)(hi - lo)]);
         sponge_absorb(sp, au);
         sponge_absorb(sp, av);
         sponge_absorb(sp, m);

@@ -163,6 +163,14 @@ JJS_HD void sponge_start(Sponge& sp, int n_absorb) {
     for (int i = 1; i < 5; i++) fq_zero(sp.s[i]);
     sp.pos = 0;
 }
+// transcripts of run-time length (multisig: 2 + 2 n and 3 + 4 n elements): the tag comes from a table the host computes
+// for the lengths a call needs (safe_tag.h), indexed by the number of absorbed elements
+JJS_HD void sponge_start_tag(Sponge& sp, const fq& tag) {
+    sp.s[0] = tag;
+#pragma unroll
+    for (int i = 1; i < 5; i++) fq_zero(sp.s[i]);
+    sp.pos = 0;
+}
 JJS_HD void sponge_absorb(Sponge& sp, const fq& x) {  // x in Montgomery form
     if (sp.pos == 4) {
         hades_permute(sp.s);

@@ -240,12 +240,8 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
         straus2<33>(acc, tabA, tabB, stride, dT, dR);
         uint32_t ru[8];
         fr_mul_short(ru, rho, u);  // |rho| * u mod r,  |rho| < 2^126
-        ext ub, sum;
-        fixedbase_mul(ub, fb, ru);
-        pniels nb;
-        ext_to_pniels(nb, ub);
-        ext_add_pniels<false>(sum, acc, nb);
-        bool ok = ext_is_identity(sum);
+        fixedbase_acc(acc, fb, ru);
+        bool ok = ext_is_identity(acc);
         if (r_implied) *r_implied = ok && rho_odd;
         return ok;
     }
@@ -298,9 +294,10 @@ JJS_HD void stage_rtest(const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_
 // d_j = H_trunc(pk_j || pk_0 .. pk_{n-1}),  agg = sum_j d_j * pk_j.  Like the reference, the signer keys are NOT
 // validated (only decoded); the aggregate is then treated exactly as the PublicKey of a single verification: its
 // affine coordinates, validity flags (identity, torsion freeness) and wire encoding are written to slot `out_index`.
-JJS_HD void aggregate_coeff_words(uint32_t* d, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j) {
+// `tags`: SAFE tags in Montgomery form indexed by the number of absorbed elements (Tables::safe_tags), valid up to 2 + 2 (hi - lo)
+JJS_HD void aggregate_coeff_words(uint32_t* d, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j, const fq* tags) {
     Sponge sp;
-    sponge_start(sp, (int)(2 + 2 * (hi - lo)));
+    sponge_start_tag(sp, tags[2 + 2 * (size_t)(hi - lo)]);
     sponge_absorb(sp, keys_u[j]);
     sponge_absorb(sp, keys_v[j]);
 #pragma unroll 1
@@ -310,18 +307,13 @@ JJS_HD void aggregate_coeff_words(uint32_t* d, const fq* keys_u, const fq* keys_
     }
     sponge_squeeze_truncated(d, sp);
 }
-JJS_HD void aggregate_coeff(int8_t* digits, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j) {
-    uint32_t d[8];
-    aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
-    recode_signed16(digits, d);
-}
 
 constexpr int AGG_GROUP = 4;  // signer keys folded per shared doubling chain (per-thread tables: AGG_GROUP x 1152 B)
 
 // acc += sum_{j in [j0, j1)} d_j * pk_j,  j1 - j0 <= AGG_GROUP;  optionally stores the coefficients d_j (8 words each)
 // `d_ready`: the coefficients were computed by an earlier kernel (stage_aggregate_coeffs) and are read from d_words
 JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j0, uint32_t j1, uint32_t* d_words,
-                            fq* tab, size_t stride, bool d_ready = false) {
+                            fq* tab, size_t stride, const fq* tags, bool d_ready = false) {
     int8_t digits[AGG_GROUP][64];
     int nb = 0;
 #pragma unroll 1
@@ -330,7 +322,7 @@ JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32
         if (d_ready) {
             for (int i = 0; i < 8; i++) d[i] = d_words[8 * (size_t)j + i];
         } else {
-            aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
+            aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j, tags);
             if (d_words)
                 for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
         }
@@ -345,29 +337,40 @@ JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32
     acc = sum;
 }
 
-// whether the signer keys [lo, hi) of an item can be aggregated at all (every key decoded, transcript within the sponge tags)
+// whether the signer keys [lo, hi) of an item can be aggregated at all: every key decodes (the reference's from_bytes);
+// the number of signers is unbounded, as in the reference
 JJS_HD bool aggregate_ready(const uint8_t* kflags, uint32_t lo, uint32_t hi) {
     bool decoded = true;
     for (uint32_t j = lo; j < hi; j++) decoded = decoded && (kflags[j] & PF_DECODED);
-    return decoded && 2 + 2 * (hi - lo) <= JJS_MAX_ABSORB;
+    return decoded;
 }
 // First half of the aggregation as a stage of its own: the delinearisation coefficients d_j of one item (n hashes of
 // 2 + 2n elements), written as 8 words each to d_words[8 j ..].  Keeping the hashing apart from the multi-scalar
 // multiplication gives two kernels with the register footprint and code size of k_challenge and k_equation.
-JJS_HD void stage_aggregate_coeffs(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, uint32_t* d_words) {
+JJS_HD void stage_aggregate_coeffs(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, uint32_t* d_words, const fq* tags) {
     if (!aggregate_ready(kflags, lo, hi)) return;
 #pragma unroll 1
     for (uint32_t j = lo; j < hi; j++) {
         uint32_t d[8];
-        aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j);
+        aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j, tags);
 #pragma unroll
         for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
     }
 }
+// the same per signer key (what k_agg_coeffs runs: one thread per key, so the hashing of a many-signer item spreads over
+// as many threads as it has signers): coefficient of key j of the item owning keys [lo, hi)
+JJS_HD void stage_aggregate_coeff_key(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, uint32_t j, uint32_t* d_words,
+                                      const fq* tags) {
+    if (!aggregate_ready(kflags, lo, hi)) return;
+    uint32_t d[8];
+    aggregate_coeff_words(d, keys_u, keys_v, lo, hi, j, tags);
+#pragma unroll
+    for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
+}
 
 // d_words: nullptr (coefficients are hashed here) or the output of stage_aggregate_coeffs for the same keys
 JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
-                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride, uint32_t* d_words = nullptr) {
+                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride, const fq* tags, uint32_t* d_words = nullptr) {
     if (!aggregate_ready(kflags, lo, hi)) {
         out_flags[out_index] = 0;
         if (agg_wire)
@@ -378,7 +381,7 @@ JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* k
     ext_identity(acc);
 #pragma unroll 1
     for (uint32_t j = lo; j < hi; j += AGG_GROUP)
-        aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tab, stride, d_words != nullptr);
+        aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tab, stride, tags, d_words != nullptr);
     fq zi, u, v, one;
     fq_inv(zi, acc.Z);
     fq_mul(u, acc.X, zi);

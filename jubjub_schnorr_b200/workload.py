@@ -27,12 +27,20 @@ OFF_CURVE = np.frombuffer(bytes.fromhex("0035c5bf742a2ff6de23941764d58bb90aa10b4
 V_GE_Q = _le(Q_INT + 5)                      # non-canonical v
 U_GE_R = _le(R_INT + 7)
 M_GE_Q = _le(Q_INT + 11)
+# Points of MIXED order, k * G + T with T of order 2, 4 or 8 ("PK = P + T", "R = valid R + T"): they decode, lie on
+# the curve and are not the identity, so only is_torsion_free() rejects them.  Constants made once with the oracle's point
+# arithmetic (tools/extract_golden.py documents the recipe: (1000003 (j + 1) + 17) * G + m * T_order); tests/test_abi.py checks them.
+MIXED_ORDER = [np.frombuffer(bytes.fromhex(h), dtype=np.uint8) for h in (
+    "f3f480af970d8742264b534b585c5c3ffda90b19a31f5287b0a533ee44cc4e18", "ebf0e228dff8472ef13783db34384a284bab12f45b0097b4c1937fefc4b0d999",
+    "6553baa30b49ed3ffcbf2c3cee5f2224a56b0862e62478ebe324cfd61ef787f3", "d52dfe7fd1a7a00ae9a3362ab56b698eae104f00a0bea2c79dff9a71bae6bbec",
+    "3879814d0e65f7fd2b4e628d8bbf7175d2b68f9f8fad8461eeb31d2879b23891", "3506cbd4a95aad5688e3d580b9da7310cf89c9a41a0e7759827abaeb39213ce1",
+    "863ff5766785670f205a1becfe28b55d68c61ee4c5bf2f2d5cade46a7744aba8", "2cadc2aee2583016fa0a9e5e4b871aaa718819e8555667b0429898d3200c763b")]
 
 # (name, status under the reference's semantics)
 CLASSES = [
     ("u_plus_one", 1), ("u_ge_r", 3), ("msg_bit_flip", 1), ("msg_ge_q", 3), ("R_from_next_item", 1), ("R_sign_flip", 1),
     ("pk_from_next_item", 1), ("pk_identity", 2), ("R_identity", 2), ("pk_order2", 2), ("pk_order4", 2), ("R_order8", 2),
-    ("pk_v_ge_q", 3), ("R_v_ge_q", 3), ("R_off_curve", 3), ("pk_off_curve", 3),
+    ("pk_v_ge_q", 3), ("R_v_ge_q", 3), ("R_off_curve", 3), ("pk_off_curve", 3), ("pk_mixed_order", 2), ("R_mixed_order", 2),
 ]
 
 
@@ -108,6 +116,10 @@ def invalidate(variant: int, pk, sig, msg, frac: float, seed: int, rank: int = 0
             sig[i, 32:64] = OFF_CURVE
         elif name == "pk_off_curve":
             pk[i, :32] = OFF_CURVE
+        elif name == "pk_mixed_order":
+            pk[i, :32] = MIXED_ORDER[j % len(MIXED_ORDER)]
+        elif name == "R_mixed_order":
+            sig[i, 32:64] = MIXED_ORDER[j % len(MIXED_ORDER)]
         expected[i] = st
         cls[i] = c
     return pk, sig, msg, expected, cls
@@ -116,7 +128,7 @@ def invalidate(variant: int, pk, sig, msg, frac: float, seed: int, rank: int = 0
 AGG_CLASSES = [
     ("u_plus_one", 1), ("u_ge_r", 3), ("msg_bit_flip", 1), ("msg_ge_q", 3), ("R_from_next_item", 1), ("R_sign_flip", 1),
     ("R_identity", 2), ("R_order8", 2), ("R_v_ge_q", 3), ("R_off_curve", 3), ("signer_key_from_next_item", 1),
-    ("signer_key_off_curve", 3), ("signer_key_v_ge_q", 3),
+    ("signer_key_off_curve", 3), ("signer_key_v_ge_q", 3), ("R_mixed_order", 2),
 ]
 
 
@@ -168,6 +180,8 @@ def make_aggregate_batch(bv: BatchVerifier, n: int, invalid_frac: float, seed: i
             pks[offsets[i + 1] - 1] = OFF_CURVE
         elif name == "signer_key_v_ge_q":
             pks[offsets[i]] = V_GE_Q
+        elif name == "R_mixed_order":
+            sig[i, 32:] = MIXED_ORDER[j % len(MIXED_ORDER)]
         expected[i] = st
         cls[i] = c
     return pks, offsets, sig, msg, expected, cls

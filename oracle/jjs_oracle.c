@@ -343,9 +343,76 @@ static void hades_permute(fe s[5]) {
     }
 }
 /* Hash::digest(Domain::Other, in)[0]; SAFE sponge rate 4 */
+/* dusk-safe tag of the IO pattern [Absorb(n), Squeeze(1)], Domain::Other for a transcript longer than the
+ * pre-generated table: BLAKE2b-512 over be32(0x80000000 | n) || be32(1) || be64(0), the digest read as a little-endian
+ * integer mod q.  multisig::aggregate_pk hashes 2 + 2 n elements for n signers (reference src/multisig.rs:393-409) and
+ * the reference puts no limit on n. */
+#define B2B_ROR(x, r) (((x) >> (r)) | ((x) << (64 - (r))))
+#define B2B_MIX(a, b, c, d, x, y) do { a += b + (x); d = B2B_ROR(d ^ a, 32); c += d; b = B2B_ROR(b ^ c, 24); \
+                                       a += b + (y); d = B2B_ROR(d ^ a, 16); c += d; b = B2B_ROR(b ^ c, 63); } while (0)
+static void blake2b512_one_block(uint8_t digest[64], const uint8_t *data, size_t len) { /* len <= 128, no key */
+    static const uint64_t iv[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                                   0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    static const uint8_t perm[10][16] = {
+        {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+        {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+        {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+        {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+        {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+    uint8_t buf[128] = {0};
+    uint64_t h[8], w[16], v[16];
+    memcpy(buf, data, len);
+    memcpy(w, buf, 128); /* little-endian host */
+    memcpy(h, iv, sizeof h);
+    h[0] ^= 0x01010040ULL;
+    memcpy(v, h, sizeof h);
+    memcpy(v + 8, iv, sizeof iv);
+    v[12] ^= (uint64_t)len;
+    v[14] ^= ~0ULL;
+    for (int round = 0; round < 12; round++) {
+        const uint8_t *p = perm[round % 10];
+        B2B_MIX(v[0], v[4], v[8], v[12], w[p[0]], w[p[1]]);
+        B2B_MIX(v[1], v[5], v[9], v[13], w[p[2]], w[p[3]]);
+        B2B_MIX(v[2], v[6], v[10], v[14], w[p[4]], w[p[5]]);
+        B2B_MIX(v[3], v[7], v[11], v[15], w[p[6]], w[p[7]]);
+        B2B_MIX(v[0], v[5], v[10], v[15], w[p[8]], w[p[9]]);
+        B2B_MIX(v[1], v[6], v[11], v[12], w[p[10]], w[p[11]]);
+        B2B_MIX(v[2], v[7], v[8], v[13], w[p[12]], w[p[13]]);
+        B2B_MIX(v[3], v[4], v[9], v[14], w[p[14]], w[p[15]]);
+    }
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+    memcpy(digest, h, 64);
+}
+static void half_mod_q(fe *o, const uint8_t bytes[32]) { /* a 256-bit little-endian value -> Fq (Montgomery) */
+    uint64_t raw[4];
+    memcpy(raw, bytes, 32);
+    while (ge256(raw, JJO_Q)) { /* at most twice: 2^256 < 3 q */
+        unsigned __int128 br = 0;
+        for (int i = 0; i < 4; i++) {
+            unsigned __int128 d = (unsigned __int128)raw[i] - JJO_Q[i] - (uint64_t)br;
+            raw[i] = (uint64_t)d;
+            br = (d >> 64) & 1;
+        }
+    }
+    f_from_raw(&FQ, o, raw);
+}
+static void safe_tag_compute(fe *tag, uint32_t n_absorb) {
+    uint8_t in[16] = {0}, digest[64];
+    uint32_t w0 = 0x80000000u | n_absorb;
+    in[0] = (uint8_t)(w0 >> 24); in[1] = (uint8_t)(w0 >> 16); in[2] = (uint8_t)(w0 >> 8); in[3] = (uint8_t)w0;
+    in[7] = 1;
+    blake2b512_one_block(digest, in, 16);
+    fe lo, hi, two256;
+    half_mod_q(&lo, digest);
+    half_mod_q(&hi, digest + 32);
+    memcpy(two256.l, JJO_Q_R2, 32); /* 2^256 mod q as a Montgomery element is R^2 mod q */
+    Q_MUL(&hi, &hi, &two256);
+    Q_ADD(tag, &lo, &hi);
+}
 static void poseidon_hash(fe *out, const fe *in, int n) {
     fe s[5];
-    memcpy(s[0].l, JJO_TAG[n], 32);
+    if (n <= JJO_MAX_ABSORB) memcpy(s[0].l, JJO_TAG[n], 32);
+    else safe_tag_compute(&s[0], (uint32_t)n);
     for (int i = 1; i < 5; i++) f_zero(&s[i]);
     int pos = 0;
     for (int i = 0; i < n; i++) {
@@ -467,7 +534,6 @@ static int verify_vargen_one(const uint8_t pk64[64], const uint8_t sig64[64], co
 }
 /* multisig::aggregate_pk (reference src/multisig.rs:154-156, 393-429) then PublicKey::verify */
 static int aggregate_pts(pt *agg, const pt *pks, int n) {
-    if (2 + 2 * n > JJO_MAX_ABSORB) return -1;
     fe *pre = (fe *)malloc(sizeof(fe) * (size_t)(2 + 2 * n));
     for (int i = 0; i < n; i++) pt_to_affine(&pre[2 + 2 * i], &pre[3 + 2 * i], &pks[i]);
     pt acc, t;
@@ -760,7 +826,6 @@ static int msig_combine_one(const uint8_t *pks32, const uint8_t *R32, const uint
     memset(sig64, 0, 64);
     for (int i = 0; i < n; i++) share_ok[i] = 0;
     if (n <= 0) return ST_INVALID_MULTISIG_TRANSCRIPT;
-    if (3 + 4 * n > JJO_MAX_ABSORB) return ST_INVALID_MULTISIG_TRANSCRIPT;
     pt *P = (pt *)malloc(sizeof(pt) * 3 * (size_t)n);
     fe *z = (fe *)malloc(sizeof(fe) * 2 * (size_t)n), m;
     pt *pks = P, *Rs = P + n, *Ss = P + 2 * n;
@@ -1029,7 +1094,7 @@ EXPORT void jjo_hades_permute(uint8_t state160[160]) { /* 5 canonical LE lanes i
 }
 EXPORT int jjo_poseidon_hash(const uint8_t *in32, int n, int truncated, uint8_t out32[32]) {
     init();
-    if (n < 1 || n > JJO_MAX_ABSORB) return 0;
+    if (n < 1) return 0;
     fe *in = (fe *)malloc(sizeof(fe) * (size_t)n), h;
     int ok = 1;
     for (int i = 0; i < n; i++) ok &= f_from_bytes(&FQ, &in[i], in32 + 32 * i);

@@ -1,5 +1,6 @@
 // Host build of the device headers (their C++ twins of the PTX blocks) so the algorithms can be checked
 // on a CPU-only machine.  Test scaffolding: never linked into libjjschnorr_b200.so.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -7,7 +8,9 @@
 #include "../../jubjub_schnorr_b200/csrc/multisig_core.cuh"
 #include "../../jubjub_schnorr_b200/csrc/sign_core.cuh"
 #include "../../jubjub_schnorr_b200/csrc/verify_core.cuh"
+#include "../../jubjub_schnorr_b200/csrc/fqs.cuh"
 #include "../../jubjub_schnorr_b200/csrc/fq_fp.cuh"
+#include "../../jubjub_schnorr_b200/csrc/safe_tag.h"
 namespace tables {
 #include "../../jubjub_schnorr_b200/csrc/jjs_constants_tables.h"
 }
@@ -65,6 +68,17 @@ static void build_fb(std::vector<niels>& out, const uint32_t uv[2][8]) {
     }
 }
 
+// SAFE tags for transcripts of run-time length, as the library's host side computes them (safe_tag.h)
+static std::vector<fq> g_tags;
+static const fq* tags_upto(size_t n_absorb) {
+    while (g_tags.size() <= n_absorb) {
+        fq t;
+        safe_tag_mont(t.l, (uint32_t)g_tags.size());
+        g_tags.push_back(t);
+    }
+    return g_tags.data();
+}
+
 static void ensure_ready() {
     if (g_ready) return;
     g_tables.root_tables = reinterpret_cast<const fq*>(tables::ROOT_TABLES);
@@ -73,16 +87,19 @@ static void ensure_ready() {
     build_fb(g_fb_gn, hconsts::GEN_NUMS_UV);
     g_tables.fb_g = g_fb_g.data();
     g_tables.fb_gn = g_fb_gn.data();
+    g_tables.safe_tags = nullptr;   // the twins pass the tag table explicitly (tags_upto)
     g_ready = true;
 }
 
 // equation stage as the kernels run it: k_equation (stage_equation_item) followed by k_rtest for the points it queued
 static int g_rtests = 0, g_equations = 0;
+static int g_eq_impl = 2;  // 1: register-operand evaluation (stage_equation_item), 2: slot-based evaluation (fqs.cuh), what k_equation runs
 static bool equation_with_rtest(int variant, int eq, const fq* pu, const fq* pv, uint8_t* pf, size_t n, size_t i, const WireField& fu, const uint32_t* cw,
                                 fq* tab) {
     bool need;
-    bool ok = stage_equation_item(variant, eq, pu, pv, pf, n, i, (variant == VAR_DOUBLE && eq == 1) ? g_tables.fb_gn : g_tables.fb_g, fu, cw, tab, tab + 36,
-                                  1, &need);
+    const niels* fb = (variant == VAR_DOUBLE && eq == 1) ? g_tables.fb_gn : g_tables.fb_g;
+    bool ok = g_eq_impl == 2 ? eq2_equation_item(eq2_slots(0), variant, eq, pu, pv, pf, n, i, fb, fu, cw, tab, tab + 36, 1, &need)
+                             : stage_equation_item(variant, eq, pu, pv, pf, n, i, fb, fu, cw, tab, tab + 36, 1, &need);
     g_equations++;
     if (need) {
         int pk_slot, r_slot, base_slot;
@@ -94,6 +111,8 @@ static bool equation_with_rtest(int variant, int eq, const fq* pu, const fq* pv,
 }
 
 extern "C" {
+void hs_set_equation_impl(int impl) { g_eq_impl = impl; }
+void hs_safe_tag(uint32_t n_absorb, uint32_t* out8) { safe_tag_mont(out8, n_absorb); }
 // counters of the deferred subgroup tests since the last call (equations evaluated, tests run)
 void hs_rtest_counters(int* equations, int* rtests) { *equations = g_equations; *rtests = g_rtests; g_equations = g_rtests = 0; }
 void hs_mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* t16) { mul_wide(t16, a, b); }
@@ -182,10 +201,17 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
     std::vector<uint32_t> cw(8 * n), kc(8 * K + 8);
     WireField fk{pks, 32}, fR{sig + 32, 64}, fmsg{msg, 32}, fu{sig, 64};
     for (size_t k = 0; k < K; k++) stage_decode(fk, k, ku.data(), kv.data(), kf.data(), k, g_tables, false);
+    size_t max_cnt = 0;
+    for (size_t i = 0; i < n; i++) max_cnt = std::max<size_t>(max_cnt, offsets[i + 1] - offsets[i]);
+    const fq* tags = tags_upto(2 + 2 * max_cnt);
     for (size_t i = 0; i < n; i++) {
         uint32_t w[8];
-        stage_aggregate_coeffs(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], kc.data());
-        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1, kc.data());
+        // the per-key form is what k_agg_coeffs runs; odd items go through the per-item form so both stay covered
+        if (i & 1) stage_aggregate_coeffs(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], kc.data(), tags);
+        else
+            for (uint32_t j = offsets[i]; j < offsets[i + 1]; j++)
+                stage_aggregate_coeff_key(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], j, kc.data(), tags);
+        stage_aggregate(ku.data(), kv.data(), kf.data(), offsets[i], offsets[i + 1], pu.data(), pv.data(), pf.data(), i, w, tab.data(), 1, tags, kc.data());
         memcpy(agg_out + 32 * i, w, 32);
         stage_decode(fR, i, pu.data(), pv.data(), pf.data(), n + i, g_tables, false);
         bool all = stage_challenge(VAR_SINGLE, pu.data(), pv.data(), pf.data(), n, i, fmsg, fu, cw.data(), itf.data());
@@ -247,9 +273,12 @@ void hs_multisig_combine(const uint8_t* pks, const uint8_t* Rs, const uint8_t* S
     WireField f[3] = {{pks, 32}, {Rs, 32}, {Ss, 32}}, fmsg{msg, 32}, fz{zs, 32};
     for (int s = 0; s < 3; s++)
         for (size_t j = 0; j < K; j++) stage_decode(f[s], j, pu.data(), pv.data(), pf.data(), s * K + j, g_tables, false);
+    size_t max_cnt = 0;
+    for (size_t s = 0; s < n; s++) max_cnt = std::max<size_t>(max_cnt, offsets[s + 1] - offsets[s]);
+    const fq* tags = tags_upto(3 + 4 * max_cnt);
     for (size_t s = 0; s < n; s++)
         stage_msig_session(pu.data(), pv.data(), pf.data(), K, offsets[s], offsets[s + 1], fmsg, fz, s, dw.data(), cdw.data(), aw.data(), ru.data(), rv.data(),
-                           sf.data(), tab.data(), 1);
+                           sf.data(), tab.data(), 1, tags);
     for (size_t s = 0; s < n; s++)
         for (uint32_t j = offsets[s]; j < offsets[s + 1]; j++)
             share_ok[j] = sf[s] == (SF_DECODED | SF_NONEMPTY) &&

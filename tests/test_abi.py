@@ -43,6 +43,52 @@ def test_no_cpu_fallback():
         BatchVerifier([0])
 
 
+def test_failed_init_leaves_an_inert_context():
+    """jjs_init without a usable device hands back a context for jjs_last_error only: every entry point must answer
+    JJS_ERR_CUDA on it instead of touching device state that was never built (round-1 advisor finding: SIGFPE)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    entry.build_cuda()
+    from jubjub_schnorr_b200 import _native
+    lib = _native.lib()
+    ctx = C.c_void_p()
+    assert lib.jjs_init(None, 1, C.byref(ctx)) == -2 and ctx
+    assert b"no CUDA device" in lib.jjs_last_error(ctx)
+    buf = (C.c_uint8 * 4096)()
+    off = (C.c_uint32 * 5)(0, 1, 2, 3, 4)
+    n = 4
+    calls = [
+        lambda: lib.jjs_verify_single(ctx, buf, buf, buf, n, buf, None),
+        lambda: lib.jjs_verify_double(ctx, buf, buf, buf, n, buf, None),
+        lambda: lib.jjs_verify_vargen(ctx, buf, buf, buf, n, buf, buf),
+        lambda: lib.jjs_verify_aggregate(ctx, buf, off, buf, buf, n, buf, None, None),
+        lambda: lib.jjs_verify_batch(ctx, buf, buf, buf, n, buf),
+        lambda: lib.jjs_verify_batch_double(ctx, buf, buf, buf, n, buf),
+        lambda: lib.jjs_verify_batch_vargen(ctx, buf, buf, buf, n, buf),
+        lambda: lib.jjs_verify_batch_aggregate(ctx, buf, off, buf, buf, n, buf),
+        lambda: lib.jjs_verify_mixed(ctx, (_native.Part * 1)(_native.Part(0, C.addressof(buf), None, C.addressof(buf), C.addressof(buf), n,
+                                                                          C.addressof(buf), None, None, None)), 1),
+        lambda: lib.jjs_verify_single_device(ctx, 0, buf, buf, buf, n, buf, None, None),
+        lambda: lib.jjs_verify_double_device(ctx, 0, buf, buf, buf, n, buf, None, None),
+        lambda: lib.jjs_verify_vargen_device(ctx, 0, buf, buf, buf, n, buf, None, None),
+        lambda: lib.jjs_verify_aggregate_device(ctx, 0, buf, off, off, buf, buf, n, buf, None, None, None),
+        lambda: lib.jjs_status_bitmap_device(ctx, 0, buf, n, buf, None),
+        lambda: lib.jjs_verify_ext(ctx, 0, buf, buf, buf, n, buf, None),
+        lambda: lib.jjs_points_to_ext(ctx, buf, buf, n, buf),
+        lambda: lib.jjs_challenge_only(ctx, 0, buf, buf, buf, n, buf),
+        lambda: lib.jjs_subgroup_check(ctx, buf, n, 0, buf),
+        lambda: lib.jjs_sign_batch(ctx, 0, buf, buf, None, buf, n, buf, buf),
+        lambda: lib.jjs_sign_aggregate_batch(ctx, buf, off, buf, buf, n, buf, buf),
+        lambda: lib.jjs_multisig_combine(ctx, buf, buf, buf, buf, off, buf, n, None, buf, None, None),
+    ]
+    for i, call in enumerate(calls):
+        assert call() == -2, i
+    assert b"no CUDA device" in lib.jjs_last_error(ctx)      # the reason survives the refused calls
+    assert lib.jjs_device_count(ctx) == 0
+    lib.jjs_destroy(ctx)
+
+
 def test_product_package_does_not_touch_the_oracle():
     pkg = os.path.join(ROOT, "jubjub_schnorr_b200")
     for base, _, files in os.walk(pkg):
@@ -76,6 +122,19 @@ def test_workload_classes_have_the_stated_status(variant, gen, ver):
     st, _ = ver(pk, sig, msg)
     assert np.array_equal(st, exp)
     assert set(np.unique(cls).tolist()) == set(range(-1, len(wl.CLASSES)))
+
+
+def test_mixed_order_constants_of_the_workload():
+    """workload.MIXED_ORDER: on the curve, not of small order, not in the prime-order subgroup; the torsion part has order 2, 4 or 8."""
+    from jubjub_schnorr_b200 import workload as wl
+    orders = set()
+    for enc in wl.MIXED_ORDER:
+        p = o.point_from_bytes(enc.tobytes())
+        assert p is not None and not o.point_is_valid(p)
+        t = o.pmul(p, o.R_ORDER)
+        assert t != o.IDENTITY and o.pmul(p, 8) != o.IDENTITY
+        orders.add(next(k for k in (2, 4, 8) if o.pmul(t, k) == o.IDENTITY))
+    assert orders == {2, 4, 8}
 
 
 def test_base58_codec_matches_reference_strings():

@@ -64,7 +64,8 @@ def test_c_oracle_primitives_match_python():
         assert co.fq_mul(a, b) == a * b % o.Q
     st = [int.from_bytes(rng.bytes(32), "little") % o.Q for _ in range(5)]
     assert co.hades_permute(st) == o.hades_permute(st)
-    for n in (1, 4, 5, 7, 8, 10, 15, 16, 17):
+    # 131+: beyond the generated tag table, the C port derives the SAFE tag itself (BLAKE2b), as hashlib does for the Python one
+    for n in (1, 4, 5, 7, 8, 10, 15, 16, 17, 130, 131, 132, 402, 803):
         ins = [int.from_bytes(rng.bytes(32), "little") % o.Q for _ in range(n)]
         assert co.poseidon_hash(ins) == o.poseidon_hash_truncated(ins)
         assert co.poseidon_hash(ins, truncated=False) == o.poseidon_hash(ins)
@@ -125,6 +126,16 @@ def test_c_oracle_aggregate_matches_python():
         ps, pc, pa = o.verify_aggregate([pks[j].tobytes() for j in range(off[i], off[i + 1])], sig[i].tobytes(), msg[i].tobytes())
         assert ps == st[i] and (pc or bytes(32)) == c[i].tobytes() and pa == agg[i].tobytes()
     assert st.tolist()[:3] == [0, 0, 1]
+
+
+def test_c_oracle_aggregate_has_no_signer_limit():
+    """multisig::aggregate_pk takes any number of signers (reference src/multisig.rs:393-429); 65 and 200 lie beyond the 64 of round 1."""
+    signers = [65, 200]
+    pks, off, sig, msg = co.gen_aggregate(23, signers)
+    st, c, agg = co.verify_aggregate(pks, off, sig, msg)
+    assert st.tolist() == [0, 0]
+    ps, pc, pa = o.verify_aggregate([pks[j].tobytes() for j in range(off[0], off[1])], sig[0].tobytes(), msg[0].tobytes())
+    assert ps == 0 and pc == c[0].tobytes() and pa == agg[0].tobytes()
 
 
 def test_generated_batches_are_deterministic_and_shardable():

@@ -17,7 +17,10 @@ def bv():
         yield v
 
 
-@pytest.mark.parametrize("variant,log2n", [(0, 20), (1, 19), (2, 19)])
+SPOT = 1 << 14   # items per variant that go to the CPU oracle at full size
+
+
+@pytest.mark.parametrize("variant,log2n", [(0, 20), (1, 20), (2, 19)])   # BASELINE.json configs[1], configs[2], the var-generator half of configs[3]
 def test_full_size_batch_properties(bv, variant, log2n):
     from jubjub_schnorr_b200 import workload as wl
     n = 1 << log2n
@@ -32,10 +35,14 @@ def test_full_size_batch_properties(bv, variant, log2n):
     st_p, c_p = ver(pk[perm], sig[perm], msg[perm], True)
     assert np.array_equal(st_p, st[perm]) and np.array_equal(c_p, c[perm])
     # oracle spot check
-    idx = np.random.default_rng(2).choice(n, size=1024, replace=False)
+    # every invalid item plus random valid ones, so that each tampering class reaches the oracle several hundred times
+    rng = np.random.default_rng(2)
+    bad = np.nonzero(cls >= 0)[0]
+    idx = np.unique(np.concatenate([rng.choice(bad, size=SPOT // 2, replace=False), rng.choice(n, size=SPOT // 2, replace=False)]))
     over = {0: co.verify_single, 1: co.verify_double, 2: co.verify_vargen}[variant]
     st_o, c_o = over(pk[idx], sig[idx], msg[idx])
     assert np.array_equal(st_o, st[idx]) and np.array_equal(c_o, c[idx])
+    assert set(np.unique(cls[idx]).tolist()) == set(range(-1, len(wl.CLASSES)))
 
 
 def test_device_pointer_entry_matches_host_entry(bv):
@@ -106,6 +113,60 @@ def test_aggregate_workload_full_size(bv):
     assert np.array_equal(d_st.cpu().numpy(), expected)
 
 
+def _agg_subset(pks, off, sel):
+    sub_off = np.zeros(len(sel) + 1, dtype=np.uint32)
+    keys = []
+    for j, i in enumerate(sel):
+        keys.append(pks[off[i]:off[i + 1]])
+        sub_off[j + 1] = sub_off[j] + (off[i + 1] - off[i])
+    return np.concatenate(keys), sub_off
+
+
+def test_mixed4_full_size_one_call(bv):
+    """BASELINE.json configs[3]: 2^19 var-generator items (a distinct generator each) + 2^19 aggregate-key items (2-4 signers), 5 % invalid,
+    through ONE jjs_verify_mixed call: expectation by construction for every item, an oracle spot check per kind, and equality with the
+    per-kind entry points."""
+    from jubjub_schnorr_b200 import batch as B
+    from jubjub_schnorr_b200 import workload as wl
+    n = 1 << 19
+    pk, sig, msg, exp_v, cls_v = wl.make_batch(bv, B.VARGEN, n, 0.05, seed=0x44)
+    pks, off, asig, amsg, exp_a, cls_a = wl.make_aggregate_batch(bv, n, 0.05, seed=0x45)
+    res = bv.verify_mixed([(B.VARGEN, pk, sig, msg), (B.AGGREGATE, pks, asig, amsg, off)], want_challenge=True, want_bitmap=True)
+    assert np.array_equal(res[0]["status"], exp_v) and np.array_equal(res[1]["status"], exp_a)
+    assert np.array_equal(bv.unpack_bitmap(res[0]["bitmap"], n), exp_v == 0) and np.array_equal(bv.unpack_bitmap(res[1]["bitmap"], n), exp_a == 0)
+    rng = np.random.default_rng(4)
+    idx = np.unique(np.concatenate([rng.choice(np.nonzero(cls_v >= 0)[0], size=SPOT // 4, replace=False), rng.choice(n, size=SPOT // 4, replace=False)]))
+    st_o, c_o = co.verify_vargen(pk[idx], sig[idx], msg[idx])
+    assert np.array_equal(st_o, res[0]["status"][idx]) and np.array_equal(c_o, res[0]["c"][idx])
+    sel = np.unique(np.concatenate([rng.choice(np.nonzero(cls_a >= 0)[0], size=SPOT // 8, replace=False), rng.choice(n, size=SPOT // 8, replace=False)]))
+    keys, sub_off = _agg_subset(pks, off, sel)
+    st_o, c_o, agg_o = co.verify_aggregate(keys, sub_off, asig[sel], amsg[sel])
+    assert np.array_equal(st_o, res[1]["status"][sel]) and np.array_equal(c_o, res[1]["c"][sel])
+    ok = st_o != 3
+    assert np.array_equal(agg_o[ok], res[1]["aggpk"][sel][ok])
+    st_v, c_v = bv.verify_vargen(pk, sig, msg, True)
+    assert np.array_equal(st_v, res[0]["status"]) and np.array_equal(c_v, res[0]["c"])
+    st_a, c_a, agg_a = bv.verify_aggregate(pks, off, asig, amsg, True, True)
+    assert np.array_equal(st_a, res[1]["status"]) and np.array_equal(c_a, res[1]["c"]) and np.array_equal(agg_a, res[1]["aggpk"])
+
+
+def test_mixed5_shape_one_call(bv):
+    """BASELINE.json configs[4] at one GPU's share: a mixed single / double batch (2^20 + 2^20 items, 10 % invalid) through ONE context
+    and ONE jjs_verify_mixed call, against the expectation by construction and an oracle spot check; pageable numpy buffers."""
+    from jubjub_schnorr_b200 import batch as B
+    from jubjub_schnorr_b200 import workload as wl
+    n = 1 << 20
+    pk_s, sig_s, msg_s, exp_s, cls_s = wl.make_batch(bv, B.SINGLE, n, 0.10, seed=0x51)
+    pk_d, sig_d, msg_d, exp_d, cls_d = wl.make_batch(bv, B.DOUBLE, n, 0.10, seed=0x52)
+    res = bv.verify_mixed([(B.SINGLE, pk_s, sig_s, msg_s), (B.DOUBLE, pk_d, sig_d, msg_d)], want_challenge=True)
+    assert np.array_equal(res[0]["status"], exp_s) and np.array_equal(res[1]["status"], exp_d)
+    rng = np.random.default_rng(6)
+    for r, pk, sig, msg, over in ((res[0], pk_s, sig_s, msg_s, co.verify_single), (res[1], pk_d, sig_d, msg_d, co.verify_double)):
+        idx = rng.choice(n, size=SPOT // 4, replace=False)
+        st_o, c_o = over(pk[idx], sig[idx], msg[idx])
+        assert np.array_equal(st_o, r["status"][idx]) and np.array_equal(c_o, r["c"][idx])
+
+
 def test_chunk_boundaries(bv):
     """Batches that straddle the internal 2^20-item pass and the 2^18-item copy slices of the host path."""
     from jubjub_schnorr_b200 import workload as wl
@@ -165,7 +226,11 @@ def test_one_context_over_two_devices():
     with BatchVerifier([0]) as g:
         batches = [(v, n) + tuple(wl.make_batch(g, v, n, 0.2, seed=11 * v + n)[:4]) for v, n in ((0, 300_001), (1, 70_001), (2, 65_537), (0, 33), (0, 1))]
         pts, u, tmsg, texp = wl.make_typed_single_batch(g, 150_001, 0.10)
+    with BatchVerifier([0]) as g:
+        pks, off, asig, amsg, aexp, _ = wl.make_aggregate_batch(g, 90_001, 0.05, seed=0x77)
     with BatchVerifier([0, 1]) as bv:
+        res = bv.verify_mixed([(0, batches[0][2], batches[0][3], batches[0][4]), (1, batches[1][2], batches[1][3], batches[1][4]), (3, pks, asig, amsg, off)])
+        assert np.array_equal(res[0]["status"], batches[0][5]) and np.array_equal(res[1]["status"], batches[1][5]) and np.array_equal(res[2]["status"], aexp)
         assert np.array_equal(bv.verify_ext(0, pts, u, tmsg), texp)
         for v, n, pk, sig, msg, exp in batches:
             st, _ = {0: bv.verify_single, 1: bv.verify_double, 2: bv.verify_vargen}[v](pk, sig, msg, True)

@@ -171,6 +171,66 @@ def test_aggregate_key_verify_matches_oracle(bv):
     assert st_o[:8].tolist() == [0, 0, 1, 2, 3, 2, 3, 2]
 
 
+def test_aggregate_key_has_no_signer_limit(bv):
+    """aggregate_pk over 65 and 200 signers (reference src/multisig.rs:393-429 has no limit; round 1 stopped at 64): bit-exact
+    status, challenge and aggregate key; then a batch whose signer counts straddle every bucket of the device-side ordering
+    (the CPU oracle needs seconds per many-signer item: n hashes of 2 + 2 n elements each)."""
+    signers = np.array([65, 200, 0, 64, 66, 1, 63], dtype=np.uint32)
+    pks, off, sig, msg = co.gen_aggregate(31, signers)
+    sig[4, 1] ^= 4
+    st_o, c_o, agg_o = co.verify_aggregate(pks, off, sig, msg)
+    assert st_o.tolist() == [0, 0, 2, 0, 1, 0, 0]
+    st_g, c_g, agg_g = bv.verify_aggregate(pks, off, sig, msg, True, True)
+    assert np.array_equal(st_g, st_o) and np.array_equal(c_g, c_o) and np.array_equal(agg_g, agg_o)
+    rng = np.random.default_rng(5)
+    signers = rng.integers(0, 70, size=300).astype(np.uint32)
+    pks, off, sig, msg = co.gen_aggregate(37, signers)
+    sig[::9, 0] ^= 1
+    st_o, c_o, agg_o = co.verify_aggregate(pks, off, sig, msg)
+    st_g, c_g, agg_g = bv.verify_aggregate(pks, off, sig, msg, True, True)
+    assert np.array_equal(st_g, st_o) and np.array_equal(c_g, c_o) and np.array_equal(agg_g, agg_o)
+    assert np.array_equal(bv.unpack_bitmap(bv.verify_batch_aggregate(pks, off, sig, msg), len(signers)), st_o == 0)
+
+
+def test_multisig_combine_has_no_participant_limit(bv):
+    """Sessions of 32, 40 and 100 participants (round 1 reported InvalidMultisigTranscript above 31): the reference's combine() result."""
+    signers = np.array([32, 40, 3, 100, 31], dtype=np.uint32)
+    pks, Rs, Ss, zs, off, msg = co.gen_multisig(47, signers)
+    zs[off[3] + 57, 0] ^= 1
+    st_o, bad_o, sig_o, ok_o = co.multisig_combine(pks, Rs, Ss, zs, off, msg)
+    assert st_o.tolist() == [0, 0, 0, 5, 0] and bad_o[3] == 57
+    st_g, bad_g, sig_g, ok_g = bv.multisig_combine(pks, Rs, Ss, zs, off, msg)
+    assert np.array_equal(st_g, st_o) and np.array_equal(bad_g, bad_o) and np.array_equal(sig_g, sig_o) and np.array_equal(ok_g, ok_o)
+
+
+def test_mixed_call_matches_separate_calls_and_oracle(bv):
+    """jjs_verify_mixed: four kinds in one call (BASELINE configs[3] / [4] shape) against the oracle, item by item; bitmaps per part."""
+    from jubjub_schnorr_b200 import batch as B
+    n = 3000
+    parts, oracle = [], []
+    for kind, gen, ver in ((B.SINGLE, co.gen_single, co.verify_single), (B.DOUBLE, co.gen_double, co.verify_double), (B.VARGEN, co.gen_vargen, co.verify_vargen)):
+        pk, sig, msg = gen(0xA0 + kind, n + 17 * kind)
+        name = {B.SINGLE: "single", B.DOUBLE: "double", B.VARGEN: "vargen"}[kind]
+        pk, sig, msg, _, _ = adv.make_adversarial(name, pk, sig, msg, seed=kind, frac=0.3)
+        parts.append((kind, pk, sig, msg))
+        oracle.append(ver(pk, sig, msg))
+    signers = np.random.default_rng(2).integers(1, 6, size=n // 2).astype(np.uint32)
+    pks, off, sig, msg = co.gen_aggregate(53, signers)
+    sig[::5, 2] ^= 8
+    parts.append((B.AGGREGATE, pks, sig, msg, off))
+    st_a, c_a, agg_a = co.verify_aggregate(pks, off, sig, msg)
+    parts.append((B.SINGLE, np.zeros((0, 32), np.uint8), np.zeros((0, 64), np.uint8), np.zeros((0, 32), np.uint8)))   # an empty part is fine
+    res = bv.verify_mixed(parts, want_challenge=True, want_bitmap=True)
+    for r, (st_o, c_o) in zip(res[:3], oracle):
+        assert np.array_equal(r["status"], st_o) and np.array_equal(r["c"], c_o)
+        assert np.array_equal(bv.unpack_bitmap(r["bitmap"], len(st_o)), st_o == 0)
+    assert np.array_equal(res[3]["status"], st_a) and np.array_equal(res[3]["c"], c_a) and np.array_equal(res[3]["aggpk"], agg_a)
+    assert res[4]["status"].size == 0
+    # bitmap entry points of the other kinds
+    assert np.array_equal(bv.unpack_bitmap(bv.verify_batch_double(*parts[1][1:4]), len(oracle[1][0])), oracle[1][0] == 0)
+    assert np.array_equal(bv.unpack_bitmap(bv.verify_batch_vargen(*parts[2][1:4]), len(oracle[2][0])), oracle[2][0] == 0)
+
+
 def test_gpu_signing_matches_reference_vectors(bv):
     """jjs_sign_batch reproduces the pinned signatures of reference tests/serde.rs (seed 2321) bit for bit."""
     s = KAT["serde_kat"]

@@ -170,8 +170,11 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+@pytest.mark.parametrize("impl", [2, 1])
 @pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
-def test_pipeline_twin_on_adversarial_batches(L, vi, kind):
+def test_pipeline_twin_on_adversarial_batches(L, vi, kind, impl):
+    """impl 2: the slot-based equation the kernel runs (csrc/fqs.cuh); impl 1: the register-operand evaluation kept for A/B builds."""
+    L.hs_set_equation_impl(impl)
     gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
     ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
     n = 320
@@ -180,6 +183,7 @@ def test_pipeline_twin_on_adversarial_batches(L, vi, kind):
     st, c = ver(pk, sig, msg)
     hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
     L.hs_verify(vi, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
+    L.hs_set_equation_impl(2)
     bad = np.nonzero(hst != st)[0]
     assert bad.size == 0, [(int(i), names[i], int(hst[i]), int(st[i])) for i in bad[:5]]
     assert np.array_equal(hc, c) and np.array_equal(st, exp)
@@ -280,6 +284,27 @@ def test_aggregate_twin(L):
     assert np.array_equal(hst, st) and np.array_equal(hc, c)
     ok = st != 3
     assert np.array_equal(ha[ok], agg[ok])
+
+
+def test_aggregate_twin_has_no_signer_limit(L):
+    """65 and 200 signers (transcripts of 132 and 402 elements: SAFE tags from the host-side BLAKE2b, csrc/safe_tag.h), an empty
+    signer set (identity aggregate: InvalidPoint) and a tampered many-signer item."""
+    signers = [65, 0, 200, 66]
+    pks, off, sig, msg = co.gen_aggregate(29, signers)
+    sig[3, 1] ^= 4
+    st, c, agg = co.verify_aggregate(pks, off, sig, msg)
+    assert st.tolist() == [0, 2, 0, 1]
+    n = len(signers)
+    hst, hc, ha = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8), np.zeros((n, 32), np.uint8)
+    L.hs_verify_aggregate(_p(pks), _p(off), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc), _p(ha))
+    assert np.array_equal(hst, st) and np.array_equal(hc, c) and np.array_equal(ha, agg)
+
+
+def test_safe_tags_match_hashlib(L):
+    out = (C.c_uint32 * 8)()
+    for n in (0, 1, 5, 7, 10, 130, 131, 402, 803, 1 << 20):
+        L.hs_safe_tag(n, out)
+        assert val(out) == o.safe_tag(n) * R256 % Q
 
 
 @pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
