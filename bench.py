@@ -184,8 +184,10 @@ def plan_parts(args, n_gpus_total):
     if args.workload == "mixed4":   # BASELINE.json configs[3]: var-generator + aggregate-key halves, 5 % invalid
         return [("vargen", n // 2, 0.05), ("aggregate", n // 2, 0.05)]
     if args.workload == "mixed5":   # BASELINE.json configs[4]: 2^log2n items in total over all GPUs, half single half double
-        per = max(2, n // n_gpus_total)
-        return [("single", per // 2, 0.10), ("double", per // 2, 0.10)]
+        from jubjub_schnorr_b200.sharding import shard_range
+        lo, hi = shard_range(n // 2, 0, n_gpus_total)      # the largest contiguous slice of each half (slices differ by at most one item)
+        per = max(1, hi - lo)
+        return [("single", per, 0.10), ("double", per, 0.10)]
     raise SystemExit("unknown workload")
 
 

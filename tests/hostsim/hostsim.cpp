@@ -9,7 +9,7 @@
 #include "../../jubjub_schnorr_b200/csrc/sign_core.cuh"
 #include "../../jubjub_schnorr_b200/csrc/verify_core.cuh"
 #include "../../jubjub_schnorr_b200/csrc/fqs.cuh"
-#include "../../jubjub_schnorr_b200/csrc/fq_fp.cuh"
+#include "../../tools/fq_fp.cuh"
 #include "../../jubjub_schnorr_b200/csrc/safe_tag.h"
 namespace tables {
 #include "../../jubjub_schnorr_b200/csrc/jjs_constants_tables.h"

@@ -21,7 +21,7 @@ def test_shard_ranges_cover_exactly():
 
 def _worker(rank, world, port, n, out_dir):
     import torch.distributed as dist
-    from jubjub_schnorr_b200.sharding import verify_sharded
+    from tests.sharded_verify import verify_sharded
     from oracle import c_oracle as co
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

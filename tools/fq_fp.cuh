@@ -16,7 +16,7 @@
 #include <stdint.h>
 #include <string.h>
 
-#include "fq.cuh"
+#include "../jubjub_schnorr_b200/csrc/fq.cuh"
 #if !defined(__CUDA_ARCH__)
 #include <cfenv>
 #include <cmath>

@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 
-#include "../jubjub_schnorr_b200/csrc/fq_fp.cuh"
+#include "fq_fp.cuh"
 
 using namespace jjs;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); exit(1); } } while (0)
