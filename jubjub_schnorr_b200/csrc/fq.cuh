@@ -345,94 +345,9 @@ JJS_HD void add_q_masked(uint32_t* r, const uint32_t* x, uint32_t mask) {
     add8(r, x, y);
 }
 
-// One Montgomery reduction step on the (ev, od) split representation  V = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1)).
-// Precondition: ev[0] == 0 (its low limb was cancelled by the previous step; for the first step the
-// caller presents T shifted up by one limb).  The step shifts V right by 32 bits, picks the quotient
-// digit m = -(low limb), adds m*q and appends `inject` as the new top limb:
-//     e0     = od[0] + ev[1]                       (new limb 0, carry continues into the odd chain)
-//     m      = -e0
-//     n[0..8]= ev[2..8],inject  + m*(q1,q3,q5,q7)  (new odd accumulator, limbs 1..9)
-//     od[1..8]+= m*(q0,q2,q4,q6) with e0 + m*q0 == 0 (mod 2^32)   (new even accumulator is (0, od[1..8]))
-JJS_HD void redc_step(const uint32_t* ev, uint32_t* od, uint32_t* n, uint32_t inject) {
-    // The two low limbs of q are 1 and 2^32 - 1, so their products with m need no multiplier:
-    //   m * q0 = m                 -> e0 + m == 0 (mod 2^32) with carry (e0 != 0)
-    //   m * q1 = (m - [m != 0]) * 2^32 + e0     (because -m == e0 mod 2^32)
-    // which leaves 6 wide multiplies per step on the integer-multiply pipe instead of 8.
-#if defined(__CUDA_ARCH__)
-    uint32_t e0, c0, m, h1;  // h1, c0: scratch of the asm blocks
-    asm("add.cc.u32 %9, %13, %14;\n\t"          // e0 = od0 + ev1, CF feeds the odd chain
-        "sub.u32 %10, 0, %9;\n\t"               // m = -e0
-        "min.u32 %11, %10, 1;\n\t"
-        "sub.u32 %11, %10, %11;\n\t"            // h1 = m - [m != 0]
-        "addc.cc.u32 %0, %15, %9;\n\t"          // n0 = ev2 + e0 + CF
-        "addc.cc.u32 %1, %16, %11;\n\t"         // n1 = ev3 + h1 + CF
-        "madc.lo.cc.u32 %2, %10, 0x53bda402, %17;\n\t"
-        "madc.hi.cc.u32 %3, %10, 0x53bda402, %18;\n\t"
-        "madc.lo.cc.u32 %4, %10, 0x3339d808, %19;\n\t"
-        "madc.hi.cc.u32 %5, %10, 0x3339d808, %20;\n\t"
-        "madc.lo.cc.u32 %6, %10, 0x73eda753, %21;\n\t"
-        "madc.hi.cc.u32 %7, %10, 0x73eda753, %22;\n\t"
-        "addc.u32 %8, 0, 0;"
-        : "=&r"(n[0]), "=&r"(n[1]), "=&r"(n[2]), "=&r"(n[3]), "=&r"(n[4]), "=&r"(n[5]), "=&r"(n[6]), "=&r"(n[7]), "=&r"(n[8]),
-          "=&r"(e0), "=&r"(m), "=&r"(h1), "=&r"(c0)
-        : "r"(od[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(inject));
-    // even chain: limb 0 cancels (e0 + m), its carry is (e0 != 0) == (m != 0)
-    asm("add.cc.u32 %8, %9, %10;\n\t"           // e0 + m -> 0, CF = (e0 != 0)
-        "addc.cc.u32 %0, %0, 0;\n\t"
-        "madc.lo.cc.u32 %1, %10, 0xfffe5bfe, %1;\n\t"
-        "madc.hi.cc.u32 %2, %10, 0xfffe5bfe, %2;\n\t"
-        "madc.lo.cc.u32 %3, %10, 0x09a1d805, %3;\n\t"
-        "madc.hi.cc.u32 %4, %10, 0x09a1d805, %4;\n\t"
-        "madc.lo.cc.u32 %5, %10, 0x299d7d48, %5;\n\t"
-        "madc.hi.cc.u32 %6, %10, 0x299d7d48, %6;\n\t"
-        "addc.u32 %7, %7, 0;"
-        : "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "=&r"(c0)
-        : "r"(e0), "r"(m));
-    od[0] = 0;
-    (void)h1;
-    (void)c0;
-#else
-    constexpr uint32_t Q[8] = JJS_Q_LIMBS;
-    uint64_t s = (uint64_t)od[0] + ev[1];
-    uint32_t e0 = (uint32_t)s;
-    uint64_t c = s >> 32;
-    uint32_t m = 0u - e0;
-    uint32_t h1 = m - (m != 0u ? 1u : 0u);
-    // odd chain
-    uint64_t t = (uint64_t)ev[2] + e0 + c;
-    n[0] = (uint32_t)t;
-    t = (uint64_t)ev[3] + h1 + (t >> 32);
-    n[1] = (uint32_t)t;
-    c = t >> 32;
-    const uint32_t addend[6] = {ev[4], ev[5], ev[6], ev[7], ev[8], inject};
-    for (int k = 0; k < 3; k++) {
-        uint64_t p = (uint64_t)m * Q[2 * k + 3];
-        uint64_t lo = (uint64_t)addend[2 * k] + (uint32_t)p + c;
-        n[2 * k + 2] = (uint32_t)lo;
-        uint64_t hi = (uint64_t)addend[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
-        n[2 * k + 3] = (uint32_t)hi;
-        c = hi >> 32;
-    }
-    n[8] = (uint32_t)c;
-    // even chain
-    c = (e0 != 0u) ? 1 : 0;
-    t = (uint64_t)od[1] + c;
-    od[1] = (uint32_t)t;
-    c = t >> 32;
-    for (int k = 0; k < 3; k++) {
-        uint64_t p = (uint64_t)m * Q[2 * k + 2];
-        uint64_t lo = (uint64_t)od[2 * k + 2] + (uint32_t)p + c;
-        od[2 * k + 2] = (uint32_t)lo;
-        uint64_t hi = (uint64_t)od[2 * k + 3] + (uint32_t)(p >> 32) + (lo >> 32);
-        od[2 * k + 3] = (uint32_t)hi;
-        c = hi >> 32;
-    }
-    od[8] += (uint32_t)c;
-    od[0] = 0;
-#endif
-}
-
-
+// (ev, od) split representation of a multi-limb value:  V = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1)).  A reduction step
+// expects ev[0] == 0 (its low limb was cancelled by the previous step; for the first step the caller presents T shifted up
+// by one limb), shifts V right by 32 bits and appends `inject` as the new top limb.
 // ---- additive reduction on the complement of q --------------------------------------------------------------------
 // q == 1 (mod 2^32) makes the Montgomery quotient digit of a value with low limb e0 equal to -e0.  Instead of negating
 // it (and patching the multiplier-free products of q's two low limbs with m - [m != 0]) the step below adds
@@ -589,9 +504,6 @@ JJS_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
     mad_diag8(t, a);
 }
 
-#ifndef JJS_REDC2
-#define JJS_REDC2 1
-#endif
 // r = t / 2^256 mod q for a 16-limb t < q * 2^256, fully reduced.
 JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     uint32_t ev[9], od[9], n[9];
@@ -600,7 +512,6 @@ JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     for (int i = 0; i < 8; i++) ev[i + 1] = t[i];
 #pragma unroll
     for (int i = 0; i < 9; i++) od[i] = 0;
-#if JJS_REDC2
     uint32_t M[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -613,21 +524,6 @@ JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     add8(v, ev + 1, od);
     uint32_t borrow = sub8(d, v, M);
     add_q_masked(r, d, borrow);
-#else
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        redc_step(ev, od, n, t[8 + i]);
-#pragma unroll
-        for (int k = 0; k < 9; k++) { ev[k] = od[k]; od[k] = n[k]; }
-    }
-    // value = (ev >> 32) + od, with ev[0] == 0
-    uint32_t v[8];
-    add8(v, ev + 1, od);
-    uint32_t s[8];
-    uint32_t borrow = sub_q(s, v);
-#pragma unroll
-    for (int i = 0; i < 8; i++) r[i] = borrow ? v[i] : s[i];
-#endif
 }
 
 // r = v / 2^32 mod q for a 9-limb v < 2^32 * q (one Montgomery step; used after small-integer linear maps)
@@ -638,12 +534,16 @@ JJS_HD void redc_one(uint32_t* r, const uint32_t* v) {
     for (int i = 0; i < 8; i++) ev[i + 1] = v[i];
 #pragma unroll
     for (int i = 0; i < 9; i++) od[i] = 0;
-    redc_step(ev, od, n, v[8]);
-    uint32_t w[8], s[8];
+    uint32_t e0;
+    redc_step2(ev, od, n, v[8], e0);
+    // (v + e0 qbar) / 2^32 = r + e0 2^224 with r in (-q, q): take e0 off limb 7, add q back on a borrow
+    uint32_t w[8], m[8], d[8];
     add8(w, od + 1, n);
-    uint32_t borrow = sub_q(s, w);
 #pragma unroll
-    for (int i = 0; i < 8; i++) r[i] = borrow ? w[i] : s[i];
+    for (int i = 0; i < 7; i++) m[i] = 0;
+    m[7] = e0;
+    uint32_t borrow = sub8(d, w, m);
+    add_q_masked(r, d, borrow);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,7 +18,6 @@
 #include "multisig_core.cuh"
 #include "sign_core.cuh"
 #include "verify_core.cuh"
-#include "fqs.cuh"
 #include "safe_tag.h"
 
 namespace tables {
@@ -29,6 +28,21 @@ using namespace jjs;
 
 namespace {
 
+// The slot-based evaluation of the verification equation (csrc/fqs.cuh: field elements in shared memory, persistent kernel) is a
+// compile-time alternative.  Measured on B200: it executes 6 % fewer multiply-pipe cycles and runs 4-7 %
+// slower than the register-operand kernel, so it is off; tests/hostsim keeps its twin under test either way.
+#ifndef JJS_EQ_V2
+#define JJS_EQ_V2 0
+#endif
+#if JJS_EQ_V2
+#include "fqs.cuh"
+#else
+namespace jjs { constexpr int EQ2_TAB_FQ = 32; }
+#ifndef JJS_EQ_BLOCK
+#define JJS_EQ_BLOCK 128
+#endif
+#endif
+
 #ifndef JJS_BLOCK
 #define JJS_BLOCK 128
 #endif
@@ -38,6 +52,9 @@ constexpr int BLOCK = JJS_BLOCK;
 #endif
 #ifndef JJS_DEC_MINBLOCKS
 #define JJS_DEC_MINBLOCKS 4
+#endif
+#ifndef JJS_EQ_PERSISTENT
+#define JJS_EQ_PERSISTENT 0   // measured (gpurun_out/ab2.log): -22 % DRAM reads but +6 % time; off
 #endif
 constexpr size_t CHUNK_ITEMS = size_t(1) << 20;   // items per pipeline pass
 constexpr size_t TAB_THREADS = size_t(1) << 20;   // threads served by the per-thread table scratch (four tables of 1152 B each)
@@ -242,21 +259,33 @@ __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int varian
                                                     size_t first, size_t count, const uint32_t* list, const uint32_t* lcount, WireField usc,
                                                     const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T,
                                                     uint32_t* rlist, uint32_t* rcount) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // Persistent form (JJS_EQ_PERSISTENT): the grid is one wave of resident CTAs and every thread walks the work list with the
+    // grid's stride, so the two per-thread tables live in a scratch indexed by RESIDENT thread (stride = gridDim.x * blockDim.x,
+    // ~130 MB in all, close to the L2's size) instead of by equation (600 MB per 2^18-item sub-chunk).
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int neq = variant == VAR_DOUBLE ? 2 : 1;
-    size_t g = first + t;
-    if (t >= count || g >= (size_t)neq * *lcount) return;
-    int eq = (int)(g % neq);
-    size_t item = list[g / neq];
-    bool need_r_test;
-    bool ok = stage_equation_item(variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
-                                  tab + t, tab + 36 * stride + t, stride, &need_r_test);
-    if (need_r_test) {
-        int pk_slot, r_slot, base_slot;
-        equation_slots(variant, eq, pk_slot, r_slot, base_slot);
-        rlist[atomicAdd(rcount, 1u)] = (uint32_t)((size_t)r_slot * n + item);
+    const size_t total = (size_t)neq * *lcount, end = first + count < total ? first + count : total;
+#if JJS_EQ_PERSISTENT
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (size_t g = first + t; g < end; g += step) {
+#else
+    {
+        const size_t g = first + t;
+        if (t >= count || g >= end) return;
+#endif
+        int eq = (int)(g % neq);
+        size_t item = list[g / neq];
+        bool need_r_test;
+        bool ok = stage_equation_item(variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
+                                      tab + t, tab + 36 * stride + t, stride, &need_r_test);
+        if (need_r_test) {
+            int pk_slot, r_slot, base_slot;
+            equation_slots(variant, eq, pk_slot, r_slot, base_slot);
+            rlist[atomicAdd(rcount, 1u)] = (uint32_t)((size_t)r_slot * n + item);
+        }
+        eqflags[(size_t)eq * n + item] = ok ? 1 : 0;
     }
-    eqflags[(size_t)eq * n + item] = ok ? 1 : 0;
 }
 
 // The same stage on the slot-based evaluation (fqs.cuh): field elements in shared memory, addressed by handle, so that no
@@ -266,9 +295,7 @@ __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int varian
 #ifndef JJS_EQ2_MINBLOCKS
 #define JJS_EQ2_MINBLOCKS 4
 #endif
-#ifndef JJS_EQ_V2
-#define JJS_EQ_V2 0   // measured (profiles/r02_*): the register-operand kernel is 4-7 % faster; the slot-based one stays as a tested alternative
-#endif
+#if JJS_EQ_V2
 __global__ void __launch_bounds__(JJS_EQ_BLOCK, JJS_EQ2_MINBLOCKS) k_equation2(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n,
                                                                                 const uint32_t* list, const uint32_t* lcount, WireField usc,
                                                                                 const uint32_t* cwords, uint8_t* eqflags, fq* tab, Tables T,
@@ -292,6 +319,8 @@ __global__ void __launch_bounds__(JJS_EQ_BLOCK, JJS_EQ2_MINBLOCKS) k_equation2(i
         eqflags[(size_t)eq * n + item] = ok ? 1 : 0;
     }
 }
+
+#endif  // JJS_EQ_V2
 
 // deferred subgroup tests: thread t < *rcount tests point rlist[t]
 __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_rtest(const fq* pts_u, const fq* pts_v, uint8_t* pflags, const uint32_t* rlist,
@@ -494,6 +523,7 @@ struct DeviceState {
     // persistent equation kernel: one wave of resident CTAs, two per-thread tables per resident thread, one such scratch
     // per compute stream (the two sub-chunk streams may run their equation kernels back to back or side by side)
     fq* eqtab = nullptr;
+    size_t eqtab_half = 0;         // elements per stream's scratch
     int eq_grid = 0;
     AggScratch agg[2];
     // staging of the host-buffer entry points: one grow-only device buffer, carved up per call
@@ -513,7 +543,7 @@ struct Region {
 };
 inline Region region_of(const DeviceState& d, size_t first_item, size_t cap, int half) {
     return Region{d.pts_u + 4 * first_item, d.pts_v + 4 * first_item, d.tab + first_item,
-                  d.eqtab + (size_t)(half & 1) * 2 * EQ2_TAB_FQ * (size_t)d.eq_grid * JJS_EQ_BLOCK, d.pflags + 4 * first_item, d.iflags + first_item,
+                  d.eqtab + (size_t)(half & 1) * d.eqtab_half, d.pflags + 4 * first_item, d.iflags + first_item,
                   d.eqflags + 2 * first_item, d.cwords + 8 * first_item, d.rlist + 2 * first_item, d.rcount + 4 * (half & 1), d.eqlist + 2 * first_item, cap,
                   half & 1};
 }
@@ -609,14 +639,21 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     {
         cudaDeviceProp prop;
         JJS_CUDA(ctx, cudaGetDeviceProperties(&prop, d.device));
+        int per_sm = 0;
+#if JJS_EQ_V2
         const size_t smem = sizeof(uint4) * 2 * EQ2_SLOTS * JJS_EQ_BLOCK;
         JJS_CUDA(ctx, cudaFuncSetAttribute(k_equation2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         JJS_CUDA(ctx, cudaFuncSetAttribute(k_equation2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        int per_sm = 0;
         JJS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_equation2, JJS_EQ_BLOCK, smem));
-        if (per_sm < 1) return fail(ctx, JJS_ERR_CUDA, "k_equation2 does not fit on an SM of device %d", d.device);
+        const size_t per_thread = 2 * EQ2_TAB_FQ, block = JJS_EQ_BLOCK;
+#else
+        JJS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_equation, BLOCK, 0));
+        const size_t per_thread = 2 * 36, block = BLOCK;
+#endif
+        if (per_sm < 1) return fail(ctx, JJS_ERR_CUDA, "the equation kernel does not fit on an SM of device %d", d.device);
         d.eq_grid = per_sm * prop.multiProcessorCount;
-        JJS_CUDA(ctx, cudaMalloc(&d.eqtab, sizeof(fq) * 2 * 2 * EQ2_TAB_FQ * (size_t)d.eq_grid * JJS_EQ_BLOCK));
+        d.eqtab_half = per_thread * (size_t)d.eq_grid * block;
+        JJS_CUDA(ctx, cudaMalloc(&d.eqtab, sizeof(fq) * 2 * d.eqtab_half));
     }
     return JJS_SUCCESS;
 }
@@ -740,6 +777,14 @@ int enqueue_equations(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant
         const unsigned grid = (unsigned)(want < (size_t)d.eq_grid ? want : (size_t)d.eq_grid);
         k_equation2<<<grid, JJS_EQ_BLOCK, smem, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, R.eqlist, R.rcount + 2, fu, R.cwords, R.eqflags,
                                                          R.eqtab, T, R.rlist, R.rcount);
+        ctx->launches++;
+    }
+#elif JJS_EQ_PERSISTENT
+    {
+        const size_t want = blocks_for(neq * m);
+        const unsigned grid = (unsigned)(want < (size_t)d.eq_grid ? want : (size_t)d.eq_grid);
+        k_equation<<<grid, BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, 0, neq * m, R.eqlist, R.rcount + 2, fu, R.cwords, R.eqflags,
+                                              R.eqtab, (size_t)d.eq_grid * BLOCK, T, R.rlist, R.rcount);
         ctx->launches++;
     }
 #else

@@ -16,7 +16,11 @@ variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "0").split(",
 n = 1 << (int(sys.argv[2]) if len(sys.argv) > 2 else 20)
 with BatchVerifier([0]) as bv:
     for variant in variants:
-        pk, sig, msg, exp, _ = wl.make_batch(bv, variant, n, 0.10, seed=0xB200)
+        pk, sig, msg, exp, cls = wl.make_batch(bv, variant, n, 0.10, seed=0xB200)
+        # units of the kernels (what the ncu counts are divided by): decoded points, work-listed items, evaluated equations
+        sig_only = np.array([nm.startswith("R_") and st == 2 for nm, st in wl.CLASSES], dtype=bool)
+        listed = int(((exp <= 1) | ((cls >= 0) & sig_only[np.clip(cls, 0, len(wl.CLASSES) - 1)])).sum())
+        units = {"k_decode": n * (2, 4, 3)[variant], "k_challenge": listed, "k_equation": listed * (1, 2, 1)[variant]}
         dev = torch.device("cuda", 0)
         d = [torch.from_numpy(x).to(dev) for x in (pk, sig, msg)]
         st = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -37,4 +41,4 @@ with BatchVerifier([0]) as bv:
         torch.cuda.synchronize()
         bv.profile(False)
         print(os.path.basename(os.environ.get("JJS_B200_LIB", "default")), "variant", variant, "step_ms", round(whole, 3),
-              {k: round(v[0] / 4, 3) for k, v in bv.profile_collect().items()}, "mismatches", int((st.cpu().numpy() != exp).sum()), flush=True)
+              {k: round(v[0] / 4, 3) for k, v in bv.profile_collect().items()}, "mismatches", int((st.cpu().numpy() != exp).sum()), "units", units, flush=True)
