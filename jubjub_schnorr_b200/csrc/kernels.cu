@@ -20,14 +20,6 @@
 #include "verify_core.cuh"
 #include "safe_tag.h"
 
-namespace tables {
-#include "jjs_constants_tables.h"
-}
-
-using namespace jjs;
-
-namespace {
-
 // The slot-based evaluation of the verification equation (csrc/fqs.cuh: field elements in shared memory, persistent kernel) is a
 // compile-time alternative.  Measured on B200: it executes 6 % fewer multiply-pipe cycles and runs 4-7 %
 // slower than the register-operand kernel, so it is off; tests/hostsim keeps its twin under test either way.
@@ -37,11 +29,18 @@ namespace {
 #if JJS_EQ_V2
 #include "fqs.cuh"
 #else
-namespace jjs { constexpr int EQ2_TAB_FQ = 32; }
 #ifndef JJS_EQ_BLOCK
 #define JJS_EQ_BLOCK 128
 #endif
 #endif
+
+namespace tables {
+#include "jjs_constants_tables.h"
+}
+
+using namespace jjs;
+
+namespace {
 
 #ifndef JJS_BLOCK
 #define JJS_BLOCK 128
