@@ -47,6 +47,8 @@ def group(op):
 
 if __name__ == "__main__":
     tag = sys.argv[1]
+    outdir = os.environ.get("JJS_PROFILE_OUT", os.path.join(ROOT, "profiles"))   # on the GPU box: a directory under gpurun_out/
+    os.makedirs(outdir, exist_ok=True)
     out = {"per_unit": {}, "instructions_per_unit": {}, "non_multiply_imad_share": {}, "how": "ncu --set full --import-source on, source page, 'Instructions Executed' (warp level) x 32 / units"}
     for spec in sys.argv[2:]:
         kind, kernel, units, path = spec.split(":", 3)
@@ -60,13 +62,13 @@ if __name__ == "__main__":
         out["per_unit"].setdefault(kind, {})[kernel] = wide * 32.0 / units
         out["instructions_per_unit"].setdefault(kind, {})[kernel] = total * 32.0 / units
         out["non_multiply_imad_share"].setdefault(kind, {})[kernel] = groups["multiply pipe: other IMAD forms (moves, carries, adds)"] / max(1, total)
-        with open(os.path.join(ROOT, "profiles", f"{tag}_{kind}_{kernel}_opcode_mix.txt"), "w") as f:
+        with open(os.path.join(outdir, f"{tag}_{kind}_{kernel}_opcode_mix.txt"), "w") as f:
             f.write(f"warp instructions executed: {total}  ({total * 32.0 / units:.0f} thread instructions per unit, {units} units)\n")
             for g, v in groups.most_common():
                 f.write(f"  {g:58s} {v:12d}  {100.0 * v / max(1, total):5.1f} %\n")
             f.write("top opcodes:\n")
             for op, v in by.most_common(16):
                 f.write(f"  {op:28s} {v:14d}  {100.0 * v / max(1, total):5.1f} %\n")
-    with open(os.path.join(ROOT, "profiles", f"{tag}_executed_mac32.json"), "w") as f:
+    with open(os.path.join(outdir, f"{tag}_executed_mac32.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out["per_unit"]))

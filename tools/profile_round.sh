@@ -32,6 +32,25 @@ for r in v0 v1 v2 agg; do
     ncu -i $out/${tag}_prof_$r.ncu-rep --page source --csv --kernel-name regex:"$k" > $out/${tag}_src_${r}_$k.csv 2>/dev/null
     [ -s $out/${tag}_src_${r}_$k.csv ] || rm -f $out/${tag}_src_${r}_$k.csv
   done
-  [ $r = v0 ] || rm -f $out/${tag}_prof_$r.ncu-rep      # keep one report (64 MiB limit on what comes back)
 done
+# executed-instruction mix per kernel and variant, computed here: the source pages and the reports are too big to travel (64 MiB)
+JJS_PROFILE_OUT=$out/${tag}_profiles python - "$tag" "$out" <<'PY'
+import ast, os, re, subprocess, sys
+tag, out = sys.argv[1], sys.argv[2]
+specs = []
+for v, kind in ((0, "single"), (1, "double"), (2, "vargen")):
+    try:
+        line = [l for l in open(f"{out}/{tag}_units_{v}.log") if "units" in l][-1]
+        units = ast.literal_eval(line[line.index("units") + 5:].strip())
+    except Exception as e:
+        print("no units for", kind, e)
+        continue
+    for k, n in units.items():
+        path = f"{out}/{tag}_src_v{v}_{k}.csv"
+        if os.path.exists(path):
+            specs.append(f"{kind}:{k}:{n // 4 if False else n}:{path}")
+# the captures ran at 2^18 items: time_stages printed the units of THAT run
+subprocess.check_call([sys.executable, "tools/ncu_executed.py", tag] + specs)
+PY
+rm -f $out/${tag}_src_*.csv $out/${tag}_prof_*.ncu-rep
 ls -la $out | grep $tag
