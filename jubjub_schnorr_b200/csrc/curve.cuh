@@ -482,15 +482,16 @@ JJS_HD void straus2(ext& r, const fq* tabA, const fq* tabB, size_t stride, const
     r = acc;
 }
 
-// acc = sum_b sum_i 16^i d[b][i] * P_b for NB <= 4 variable bases (64 signed radix-16 digits each) sharing one doubling
-// chain; table b lives at tab + b * 36 * stride.  acc.T is defined on return.
-JJS_HD void straus_multi(ext& r, int nb, const fq* tab, size_t stride, const int8_t (*digits)[64]) {
+// acc = sum_b sum_i 16^i d[b][i] * P_b for NB <= 4 variable bases (`nd` <= 64 signed radix-16 digits each) sharing one doubling
+// chain; table b lives at tab + b * 36 * stride.  acc.T is defined on return.  The last addition of a window is followed by
+// a doubling, which does not read T, so it skips that product in every window but the last.
+JJS_HD void straus_multi(ext& r, int nb, const fq* tab, size_t stride, const int8_t (*digits)[64], int nd = 64) {
     ext acc, t;
     pniels n;
     ext_identity(acc);
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        if (i != 63) {
+    for (int i = nd - 1; i >= 0; i--) {
+        if (i != nd - 1) {
             ext_dbl<false>(t, acc);
             ext_dbl<false>(acc, t);
             ext_dbl<false>(t, acc);
@@ -501,7 +502,8 @@ JJS_HD void straus_multi(ext& r, int nb, const fq* tab, size_t stride, const int
             int d = digits[b][i];
             pniels_load(n, tab + (size_t)b * 36 * stride, stride, d < 0 ? -d : d);
             pniels_cneg(n, d < 0);
-            ext_add_pniels<true>(t, acc, n);
+            if (b == nb - 1 && i != 0) ext_add_pniels<false>(t, acc, n);
+            else ext_add_pniels<true>(t, acc, n);
             acc = t;
         }
     }

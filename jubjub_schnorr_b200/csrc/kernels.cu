@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(BLOCK) k_subgroup_check(WireField pts, size_t 
 
 // thread T = first + t < neq * *count : equation T % neq of item list[T / neq].  Signature points whose subgroup
 // membership the equation did not establish are appended to `rlist` (indices into the point arrays) for k_rtest.
+// (instantiated per kind of equation: MODE 0 fixed base -- single, double -- and MODE 1 variable base -- var-gen)
+template <int MODE>
 __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n,
                                                     size_t first, size_t count, const uint32_t* list, const uint32_t* lcount, WireField usc,
                                                     const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T,
@@ -276,8 +278,8 @@ __global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int varian
         int eq = (int)(g % neq);
         size_t item = list[g / neq];
         bool need_r_test;
-        bool ok = stage_equation_item(variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
-                                      tab + t, tab + 36 * stride + t, stride, &need_r_test);
+        bool ok = stage_equation_item<MODE>(variant, eq, pts_u, pts_v, pflags, n, item, (variant == VAR_DOUBLE && eq == 1) ? T.fb_gn : T.fb_g, usc, cwords,
+                                            tab + t, tab + 36 * stride + t, stride, &need_r_test);
         if (need_r_test) {
             int pk_slot, r_slot, base_slot;
             equation_slots(variant, eq, pk_slot, r_slot, base_slot);
@@ -646,8 +648,8 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
         JJS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_equation2, JJS_EQ_BLOCK, smem));
         const size_t per_thread = 2 * EQ2_TAB_FQ, block = JJS_EQ_BLOCK;
 #else
-        JJS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_equation, BLOCK, 0));
-        const size_t per_thread = 2 * 36, block = BLOCK;
+        JJS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_equation<1>, BLOCK, 0));
+        const size_t per_thread = 3 * 36, block = BLOCK;   // the var-gen equation builds three tables
 #endif
         if (per_sm < 1) return fail(ctx, JJS_ERR_CUDA, "the equation kernel does not fit on an SM of device %d", d.device);
         d.eq_grid = per_sm * prop.multiProcessorCount;
@@ -782,15 +784,16 @@ int enqueue_equations(jjs_ctx* ctx, DeviceState& d, const Region& R, int variant
     {
         const size_t want = blocks_for(neq * m);
         const unsigned grid = (unsigned)(want < (size_t)d.eq_grid ? want : (size_t)d.eq_grid);
-        k_equation<<<grid, BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, 0, neq * m, R.eqlist, R.rcount + 2, fu, R.cwords, R.eqflags,
-                                              R.eqtab, (size_t)d.eq_grid * BLOCK, T, R.rlist, R.rcount);
+        (variant == VAR_VARGEN ? k_equation<1> : k_equation<0>)<<<grid, BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, 0, neq * m, R.eqlist, R.rcount + 2, fu,
+                                                                                            R.cwords, R.eqflags, R.eqtab, (size_t)d.eq_grid * BLOCK, T, R.rlist, R.rcount);
         ctx->launches++;
     }
 #else
     for (size_t first = 0; first < neq * m; first += R.cap) {
         size_t cnt = neq * m - first < R.cap ? neq * m - first : R.cap;
-        k_equation<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, first, cnt, R.eqlist, R.rcount + 2, fu, R.cwords,
-                                                         R.eqflags, R.tab, TAB_THREADS, T, R.rlist, R.rcount);
+        (variant == VAR_VARGEN ? k_equation<1> : k_equation<0>)<<<blocks_for(cnt), BLOCK, 0, stream>>>(variant, R.pts_u, R.pts_v, R.pflags, m, first, cnt, R.eqlist,
+                                                                                                       R.rcount + 2, fu, R.cwords, R.eqflags, R.tab, TAB_THREADS, T, R.rlist,
+                                                                                                       R.rcount);
         ctx->launches++;
     }
 #endif

@@ -3,6 +3,7 @@
 #pragma once
 #include "consts.cuh"
 #include "fq.cuh"
+#include <cmath>
 
 namespace jjs {
 
@@ -91,11 +92,15 @@ JJS_HD double limbs_to_double(const uint32_t* a) {
 // still fits the 33 signed radix-16 digits of the equation kernel (a < 2^130, the usual case: a * rho <= r).  An odd
 // rho is what lets the equation kernel skip the subgroup test of R (verify_core.cuh, stage_equation): rho_odd reports
 // whether one was found.  tau has 5 limbs (< 2^130), rho 4.
-JJS_HD void half_gcd(uint32_t* tau5, uint32_t* rho4, bool& rho_neg, bool& rho_odd, const uint32_t* c8) {
-    uint32_t a[8], b[8], ta[4] = {0, 0, 0, 0}, tb[4] = {1, 0, 0, 0};
+// The Euclidean sequence itself: on return (a, ta) and (b, tb) are consecutive (remainder, cofactor) pairs with b < 2^126 <= a,
+//     b == (neg ? -tb : tb) * c   and   a == (neg ? ta : -ta) * c   (mod r),        ta <= tb < 2^126.
+JJS_HD void half_gcd_core(uint32_t* a, uint32_t* b, uint32_t* ta, uint32_t* tb, bool& neg, const uint32_t* c8) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { ta[i] = 0; tb[i] = 0; }
+    tb[0] = 1;
 #pragma unroll
     for (int i = 0; i < 8; i++) { a[i] = JJS_C(R_ORDER)[i]; b[i] = c8[i]; }
-    bool neg = false;
+    neg = false;
 #pragma unroll 1
     while ((b[7] | b[6] | b[5] | b[4]) != 0u || b[3] >= (1u << 30)) {
         uint32_t tmp[8];
@@ -145,12 +150,306 @@ JJS_HD void half_gcd(uint32_t* tau5, uint32_t* rho4, bool& rho_neg, bool& rho_od
         for (int i = 0; i < 4; i++) { uint32_t x = ta[i]; ta[i] = tb[i]; tb[i] = x; }
         neg = !neg;
     }
+}
+JJS_HD void half_gcd(uint32_t* tau5, uint32_t* rho4, bool& rho_neg, bool& rho_odd, const uint32_t* c8) {
+    uint32_t a[8], b[8], ta[4], tb[4];
+    bool neg;
+    half_gcd_core(a, b, ta, tb, neg, c8);
     bool prev = !(tb[0] & 1u) && (ta[0] & 1u) && (a[7] | a[6] | a[5]) == 0u && a[4] < 4u;
 #pragma unroll
     for (int i = 0; i < 4; i++) { tau5[i] = prev ? a[i] : b[i]; rho4[i] = prev ? ta[i] : tb[i]; }
     tau5[4] = prev ? a[4] : 0u;
     rho_neg = prev ? !neg : neg;
     rho_odd = (rho4[0] & 1u) != 0u;
+}
+
+// ---- three short scalars for an equation with two variable bases and a variable generator ---------------------------------
+// u*Gen + c*PK == R has no fixed base, so the half-size trick above leaves a full-size multiplier on Gen.  Multiplying the
+// equation by any z != 0 (mod r) gives the equivalent check  x*Gen + y*PK - z*R == O  with  x == z u,  y == z c  (mod r);
+// the triples (x, y, z) form a lattice of rank 3 and determinant r^2, whose short vectors have ~168-bit coordinates
+// (r^(2/3)), and a 3-table Straus interleave over 43 signed radix-16 windows then needs 168 doublings instead of 252.
+//
+// lattice3_reduce finds such a vector.  Basis: the two consecutive pairs (tau_i, rho_i) of the half-gcd of c (126-bit each),
+// extended by x_i = rho_i u mod r, and (r, 0, 0).  Reduction: greedy in the style of Semaev's rank-3 algorithm, with every
+// quotient estimated in double precision from 53-bit approximations of the coordinates and applied EXACTLY to the 256-bit
+// integers.  Every update is an integer row operation, so the vectors stay in the lattice whatever the rounding errors
+// do: floating point only steers, it cannot make the result wrong, only longer -- and a result that is too long for the
+// 43 windows (or a run that hits the round cap) makes the caller fall back to the two-table evaluation.
+struct s256 {  // signed, two's complement, little-endian limbs
+    uint32_t l[8];
+};
+JJS_HD bool s256_is_neg(const s256& a) { return (a.l[7] >> 31) != 0u; }
+JJS_HD void s256_abs(uint32_t* m, const s256& a) {
+    uint32_t z[8], n[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) z[i] = 0;
+    sub8(n, z, a.l);
+    bool neg = s256_is_neg(a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = neg ? n[i] : a.l[i];
+}
+JJS_HD void s256_negate(s256& a) {
+    uint32_t z[8], n[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) z[i] = 0;
+    sub8(n, z, a.l);
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.l[i] = n[i];
+}
+// value * 2^-130 as a double (truncation error below 2^-50 relative)
+JJS_HD double s256_to_double(const s256& a) {
+    uint32_t m[8];
+    s256_abs(m, a);
+    double d = limbs_to_double(m) * 7.34683969347875e-40;  // 2^-130
+    return s256_is_neg(a) ? -d : d;
+}
+// v -= k * (w << 32 limb_shift)   (mod 2^256: exact whenever the true result fits, which the callers' norms guarantee)
+JJS_HD void s256_submul(s256& v, const s256& w, int32_t k, int limb_shift) {
+    uint32_t ws[8], p[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ws[i] = w.l[i];
+#pragma unroll 1
+    for (int s = 0; s < limb_shift; s++) {
+#pragma unroll
+        for (int i = 7; i > 0; i--) ws[i] = ws[i - 1];
+        ws[0] = 0;
+    }
+    uint32_t mag = k < 0 ? (uint32_t)(-(int64_t)k) : (uint32_t)k;
+    uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t t = (uint64_t)mag * ws[i] + carry;
+        p[i] = (uint32_t)t;
+        carry = t >> 32;
+    }
+    uint32_t r[8];
+    if (k < 0) add8(r, v.l, p);
+    else sub8(r, v.l, p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v.l[i] = r[i];
+}
+// One vector of the working basis in floating point: coordinates (scaled by 2^-130), squared length, and its row of the
+// integer transformation that leads from the exact basis of the current round to it (entries are exact small integers).
+struct lrow {
+    double d[3], t[3], n;
+};
+JJS_HD void lrow_norm(lrow& v) { v.n = v.d[0] * v.d[0] + v.d[1] * v.d[1] + v.d[2] * v.d[2]; }
+JJS_HD double lrow_dot(const lrow& a, const lrow& b) { return a.d[0] * b.d[0] + a.d[1] * b.d[1] + a.d[2] * b.d[2]; }
+JJS_HD void lrow_swap_if(lrow& a, lrow& b, bool sw) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double x = a.d[k], y = b.d[k];
+        a.d[k] = sw ? y : x;
+        b.d[k] = sw ? x : y;
+        x = a.t[k], y = b.t[k];
+        a.t[k] = sw ? y : x;
+        b.t[k] = sw ? x : y;
+    }
+    double x = a.n, y = b.n;
+    a.n = sw ? y : x;
+    b.n = sw ? x : y;
+}
+JJS_HD double lattice_max3(double a, double b, double c) {
+    a = fabs(a), b = fabs(b), c = fabs(c);
+    double m = a > b ? a : b;
+    return m > c ? m : c;
+}
+// a quotient as a 31-bit digit at a limb shift: q ~ k 2^(32 sh)
+JJS_HD void lattice_digit(int32_t& k, int& sh, double q) {
+    double m = fabs(q), sc = 1.0;
+    sh = 0;
+#pragma unroll 1
+    while (m >= 2147483648.0 && sh < 8) {
+        m *= 2.3283064365386963e-10;
+        sc *= 2.3283064365386963e-10;
+        sh++;
+    }
+    k = (int32_t)rint(q * sc);
+}
+JJS_HD bool s256_fits_170(const s256& a) {
+    uint32_t m[8];
+    s256_abs(m, a);
+    return (m[7] | m[6]) == 0u && (m[5] >> 10) == 0u;
+}
+// t0 o0 + t1 o1 + t2 o2 for exact small integers t (as doubles)
+JJS_HD void lattice3_comb(s256& r, const double* t, const s256& o0, const s256& o1, const s256& o2) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = 0;
+    s256_submul(r, o0, -(int32_t)t[0], 0);
+    s256_submul(r, o1, -(int32_t)t[1], 0);
+    s256_submul(r, o2, -(int32_t)t[2], 0);
+}
+// takes the vector (x, y, z) if it fits the windows, has z != 0 and (when asked) an odd z
+JJS_HD bool lattice3_pick(const s256* V, bool want_odd, uint32_t* xm, uint32_t* ym, uint32_t* zm, bool& xneg, bool& yneg, bool& zneg) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nz |= V[2].l[i];
+    if (nz == 0u || (want_odd && !(V[2].l[0] & 1u))) return false;
+    if (!(s256_fits_170(V[0]) && s256_fits_170(V[1]) && s256_fits_170(V[2]))) return false;
+    s256_abs(xm, V[0]);
+    s256_abs(ym, V[1]);
+    s256_abs(zm, V[2]);
+    xneg = s256_is_neg(V[0]);
+    yneg = s256_is_neg(V[1]);
+    zneg = s256_is_neg(V[2]);
+    return true;
+}
+constexpr int LATTICE3_MAX_ROUNDS = 16, LATTICE3_INNER = 10;
+constexpr double LATTICE3_CAP = 4194304.0;   // 2^22: bound on the entries of a round's transformation (and on every quotient)
+constexpr int LATTICE3_WINDOWS = 43;         // signed radix-16 digits of a magnitude below 2^170
+#ifndef JJS_LAT_RCP
+#define JJS_LAT_RCP 1
+#endif
+// 1 / x for a positive normal x to ~40 bits (the quotient estimates need ~25): the hardware's approximate reciprocal and one
+// Newton step in place of the ~40-instruction IEEE division subroutine; the host twin divides
+JJS_HD double lattice_rcp(double x) {
+#if defined(__CUDA_ARCH__) && JJS_LAT_RCP
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y * (2.0 - x * y);
+#else
+    return 1.0 / x;
+#endif
+}
+JJS_HD double lattice_clamp(double k) {
+    k = k > LATTICE3_CAP - 1.0 ? LATTICE3_CAP - 1.0 : k;
+    return k < 1.0 - LATTICE3_CAP ? 1.0 - LATTICE3_CAP : k;
+}
+// every lane of the warp that is still reducing keeps the others in the loop (they run empty rounds), so that the exact
+// update at the end of a round is executed once per warp, not once per lane
+JJS_HD bool lattice_any(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), p) != 0;
+#else
+    return p;
+#endif
+}
+// On success: |x|, |y|, |z| < 2^170 as magnitudes (six limbs used) with their signs, z != 0, x == z u and y == z c (mod r);
+// z_odd tells whether z is odd (preferred: see verify_core.cuh, stage_equation).  Returns false if no basis vector fits.
+//
+// Organisation: Lehmer style, and uniform across a warp.  The exact basis E is touched once per ROUND: a round lifts E to
+// doubles, runs LATTICE3_INNER greedy iterations on the doubles alone while accumulating the integer transformation T (its
+// entries, and so every quotient, capped at 2^22, which leaves the estimates > 8 good bits after the cancellation that
+// goes with it; an update that would exceed the cap waits for the next round), and then replaces E by T E exactly.  One
+// iteration = order the three vectors by length; a Gauss step of the second against the shortest; then the longest against
+// the plane of the other two (2 x 2 Gram system) when that pair is well conditioned, else against the shortest alone.
+// Reducing the longest in EVERY iteration keeps all quotients small -- left alone, (r, 0, 0) would need 64-bit
+// coefficients once the other two have finished their Gauss phase.  Control flow does not depend on the data: a step that
+// does not apply has quotient 0, so the 32 lanes of a warp stay together (a first version with data-dependent branches and
+// per-lane rounds cost 8.3 ms per 2^20 equations; this one 1.5 ms, plus 0.7 ms for the half-gcd).  Taking both steps of an
+// iteration from the same state (half the dependency chain, 20 % more iterations) measured no faster; neither did replacing
+// the IEEE divisions.  Model: tools/lattice3_model.py (4-6 rounds per challenge).
+JJS_HD bool lattice3_reduce(uint32_t* xm, uint32_t* ym, uint32_t* zm, bool& xneg, bool& yneg, bool& zneg, bool& z_odd, const uint32_t* u8,
+                            const uint32_t* c8) {
+    s256 E[3][3];   // rows: basis vectors (x, y, z)
+    {
+        uint32_t a[8], b[8], ta[4], tb[4], m[8];
+        bool neg;
+        half_gcd_core(a, b, ta, tb, neg, c8);
+        // (rho1 u, tau1, rho1) with rho1 = neg ? ta : -ta, tau1 = a;  (rho2 u, tau2, rho2) with rho2 = neg ? -tb : tb, tau2 = b
+        fr_mul_short(m, ta, u8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { E[0][0].l[i] = m[i]; E[0][1].l[i] = a[i]; E[0][2].l[i] = i < 4 ? ta[i] : 0u; }
+        if (!neg) { s256_negate(E[0][0]); s256_negate(E[0][2]); }
+        fr_mul_short(m, tb, u8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { E[1][0].l[i] = m[i]; E[1][1].l[i] = b[i]; E[1][2].l[i] = i < 4 ? tb[i] : 0u; }
+        if (neg) { s256_negate(E[1][0]); s256_negate(E[1][2]); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { E[2][0].l[i] = JJS_C(R_ORDER)[i]; E[2][1].l[i] = 0; E[2][2].l[i] = 0; }
+    }
+    bool converged = false;
+#pragma unroll 1
+    for (int round = 0; round < LATTICE3_MAX_ROUNDS && lattice_any(!converged); round++) {
+        lrow A, B, C;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            A.d[k] = s256_to_double(E[0][k]);
+            B.d[k] = s256_to_double(E[1][k]);
+            C.d[k] = s256_to_double(E[2][k]);
+            A.t[k] = k == 0 ? 1.0 : 0.0;
+            B.t[k] = k == 1 ? 1.0 : 0.0;
+            C.t[k] = k == 2 ? 1.0 : 0.0;
+        }
+        lrow_norm(A);
+        lrow_norm(B);
+        lrow_norm(C);
+        {   // laggards: a vector that needs a quotient of 2^20 or more against the first one (an update the cap kept out of the
+            // previous round while the others went on shrinking) gets it exactly, 31 bits at a time; rare (3 in 10^4 challenges)
+            double ian = lattice_rcp(A.n), rb = lrow_dot(A, B) * ian, rc = lrow_dot(A, C) * ian;
+            bool bigb = fabs(rb) >= 1048576.0, bigc = fabs(rc) >= 1048576.0;
+            if (lattice_any(bigb || bigc)) {
+                int32_t kb, kc;
+                int shb, shc;
+                lattice_digit(kb, shb, bigb ? rb : 0.0);
+                lattice_digit(kc, shc, bigc ? rc : 0.0);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    s256_submul(E[1][k], E[0][k], kb, shb);
+                    s256_submul(E[2][k], E[0][k], kc, shc);
+                    B.d[k] = s256_to_double(E[1][k]);
+                    C.d[k] = s256_to_double(E[2][k]);
+                }
+                lrow_norm(B);
+                lrow_norm(C);
+            }
+        }
+#pragma unroll 1
+        for (int it = 0; it < LATTICE3_INNER; it++) {
+            lrow_swap_if(A, B, A.n > B.n);
+            lrow_swap_if(B, C, B.n > C.n);
+            lrow_swap_if(A, B, A.n > B.n);
+            double ab = lrow_dot(A, B), ac = lrow_dot(A, C), bc = lrow_dot(B, C);
+            double ian = lattice_rcp(A.n), ra = ab * ian;
+            bool want1 = fabs(ra) > 0.500001;
+            // Gauss step of B against A
+            double k = want1 ? lattice_clamp(rint(ra)) : 0.0;
+            {
+                double t0 = B.t[0] - k * A.t[0], t1 = B.t[1] - k * A.t[1], t2 = B.t[2] - k * A.t[2];
+                k = lattice_max3(t0, t1, t2) <= LATTICE3_CAP ? k : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) { B.t[j] -= k * A.t[j]; B.d[j] -= k * A.d[j]; }
+            lrow_norm(B);
+            // C against the plane of A and B, or against A alone while A and B are still close to parallel
+            ab = lrow_dot(A, B);
+            bc = lrow_dot(B, C);
+            double mn = A.n < B.n ? A.n : B.n;
+            bool well = fabs(ab) <= 0.55 * mn;
+            double idet = lattice_rcp(well ? A.n * B.n - ab * ab : 1.0);
+            double fa = well ? (ac * B.n - bc * ab) * idet : ac * ian, fb = well ? (bc * A.n - ac * ab) * idet : 0.0;
+            double qa = lattice_clamp(rint(fa)), qb = lattice_clamp(rint(fb));
+            bool want2 = qa != 0.0 || qb != 0.0;
+            {
+                double t0 = C.t[0] - qa * A.t[0] - qb * B.t[0], t1 = C.t[1] - qa * A.t[1] - qb * B.t[1], t2 = C.t[2] - qa * A.t[2] - qb * B.t[2];
+                bool fits = lattice_max3(t0, t1, t2) <= LATTICE3_CAP;
+                qa = fits ? qa : 0.0;
+                qb = fits ? qb : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) { C.t[j] -= qa * A.t[j] + qb * B.t[j]; C.d[j] -= qa * A.d[j] + qb * B.d[j]; }
+            lrow_norm(C);
+            converged = converged || (!want1 && !want2);
+        }
+        lrow_swap_if(A, B, A.n > B.n);   // E stays ordered by length
+        lrow_swap_if(B, C, B.n > C.n);
+        lrow_swap_if(A, B, A.n > B.n);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            s256 o0 = E[0][k], o1 = E[1][k], o2 = E[2][k];
+            lattice3_comb(E[0][k], A.t, o0, o1, o2);
+            lattice3_comb(E[1][k], B.t, o0, o1, o2);
+            lattice3_comb(E[2][k], C.t, o0, o1, o2);
+        }
+    }
+    // the shortest vector that fits, one with an odd z first (E is ordered by length)
+    z_odd = true;
+    if (lattice3_pick(E[0], true, xm, ym, zm, xneg, yneg, zneg) || lattice3_pick(E[1], true, xm, ym, zm, xneg, yneg, zneg) ||
+        lattice3_pick(E[2], true, xm, ym, zm, xneg, yneg, zneg))
+        return true;
+    z_odd = false;
+    return lattice3_pick(E[0], false, xm, ym, zm, xneg, yneg, zneg) || lattice3_pick(E[1], false, xm, ym, zm, xneg, yneg, zneg) ||
+           lattice3_pick(E[2], false, xm, ym, zm, xneg, yneg, zneg);
 }
 
 // signed radix-16 digits d_i in [-8, 8) of a little-endian scalar of NLIMBS limbs; writes 8 * NLIMBS + 1 digits

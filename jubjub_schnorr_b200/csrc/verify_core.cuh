@@ -12,6 +12,10 @@
 
 namespace jjs {
 
+#ifndef JJS_VARGEN_LATTICE
+#define JJS_VARGEN_LATTICE 1   // var-generator equation with three short scalars (scalar.cuh, lattice3_reduce); 0: two full-size scalars
+#endif
+
 enum Variant : int { VAR_SINGLE = 0, VAR_DOUBLE = 1, VAR_VARGEN = 2 };
 
 // point flags
@@ -216,8 +220,12 @@ JJS_HD uint8_t subgroup_check(const WireField& f, size_t i, int method, fq* tab,
 //     R torsion free            =>  check holds  <=>  u*B + c*PK == R   (rho is invertible mod r).
 // `r_implied` reports the first case: the caller may then take is_torsion_free(R) as established without testing
 // it; in every other case it must run the subgroup test on R and use the returned bool only if R passes.
-// Variable base (var-gen): u*Gen + c*PK by a 64-window Straus interleave, compared projectively with R; equality
-// with Gen, PK in the subgroup puts R there too.
+// Variable base (var-gen): three short scalars (below) over 43 windows; the fallback is u*Gen + c*PK by a 64-window Straus
+// interleave, compared projectively with R (equality with Gen, PK in the subgroup puts R there too).
+// tabA must be followed by two more per-thread tables at tabA + 36 stride (== tabB) and tabA + 72 stride.
+// MODE: -1 either kind (decided by base_slot at run time), 0 fixed base only, 1 variable base only -- the kernels instantiate the
+// two kinds separately so that neither carries the other's code and registers.
+template <int MODE = -1>
 JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t item, int pk_slot, int r_slot, int base_slot,
                            const niels* fb, const WireField& usc, const uint32_t* c_words, fq* tabA, fq* tabB, size_t stride,
                            bool* r_implied = nullptr) {
@@ -226,7 +234,7 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
 #pragma unroll
     for (int i = 0; i < 8; i++) c[i] = c_words[item * 8 + i];
     ext acc;
-    if (base_slot < 0) {
+    if (MODE == 0 || (MODE < 0 && base_slot < 0)) {
         uint32_t tau[5], rho[8];
         bool rho_neg, rho_odd;
         half_gcd(tau, rho, rho_neg, rho_odd, c);
@@ -245,6 +253,29 @@ JJS_HD bool stage_equation(const fq* pts_u, const fq* pts_v, size_t n, size_t it
         if (r_implied) *r_implied = ok && rho_odd;
         return ok;
     }
+#if JJS_VARGEN_LATTICE
+    {
+        // three short scalars (scalar.cuh, lattice3_reduce): x*Gen + y*PK - z*R == O over 43 shared-doubling windows and
+        // three per-thread tables (tabA, tabB = tabA + 36 stride, and the next one).  The same argument as above covers R:
+        // the check passing with z odd proves R torsion free and the equation; otherwise the caller tests R.
+        uint32_t xm[8], ym[8], zm[8];
+        bool xneg, yneg, zneg, z_odd;
+        if (lattice3_reduce(xm, ym, zm, xneg, yneg, zneg, z_odd, u, c)) {
+            int8_t dg[3][64];
+            recode_signed16_n<6>(dg[0], xm, xneg);
+            recode_signed16_n<6>(dg[1], ym, yneg);
+            recode_signed16_n<6>(dg[2], zm, !zneg);
+            varbase_table_build(tabA, stride, pts_u[base_slot * n + item], pts_v[base_slot * n + item]);
+            varbase_table_build(tabA + 36 * stride, stride, pts_u[pk_slot * n + item], pts_v[pk_slot * n + item]);
+            varbase_table_build(tabA + 72 * stride, stride, pts_u[r_slot * n + item], pts_v[r_slot * n + item]);
+            straus_multi(acc, 3, tabA, stride, dg, LATTICE3_WINDOWS);
+            bool ok = ext_is_identity(acc);
+            if (r_implied) *r_implied = ok && z_odd;
+            return ok;
+        }
+    }
+#endif
+    // no short vector found (never seen for hash outputs; reachable in principle): the direct evaluation
     int8_t dU[64], dC[64];
     recode_signed16(dU, u);
     recode_signed16(dC, c);
@@ -266,6 +297,7 @@ JJS_HD void equation_slots(int variant, int eq, int& pk_slot, int& r_slot, int& 
     else if (variant == VAR_DOUBLE) { pk_slot = eq; r_slot = 2 + eq; base_slot = -1; }
     else { pk_slot = 0; r_slot = 2; base_slot = 1; }
 }
+template <int MODE = -1>
 JJS_HD bool stage_equation_item(int variant, int eq, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n, size_t item, const niels* fb,
                                 const WireField& usc, const uint32_t* c_words, fq* tabA, fq* tabB, size_t stride, bool* need_r_test) {
     int pk_slot, r_slot, base_slot;
@@ -274,7 +306,7 @@ JJS_HD bool stage_equation_item(int variant, int eq, const fq* pts_u, const fq* 
     if (!point_flags_valid(pflags[pk_slot * n + item])) return false;
     if (base_slot >= 0 && !point_flags_valid(pflags[base_slot * n + item])) return false;
     bool implied = false;
-    bool ok = stage_equation(pts_u, pts_v, n, item, pk_slot, r_slot, base_slot, fb, usc, c_words, tabA, tabB, stride, &implied);
+    bool ok = stage_equation<MODE>(pts_u, pts_v, n, item, pk_slot, r_slot, base_slot, fb, usc, c_words, tabA, tabB, stride, &implied);
     uint8_t rf = pflags[r_slot * n + item];
     if (rf & PF_TORSION_PENDING) {
         if (implied) pflags[r_slot * n + item] = (uint8_t)((rf & ~PF_TORSION_PENDING) | PF_TORSION_FREE);

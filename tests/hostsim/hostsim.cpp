@@ -93,7 +93,7 @@ static void ensure_ready() {
 
 // equation stage as the kernels run it: k_equation (stage_equation_item) followed by k_rtest for the points it queued
 static int g_rtests = 0, g_equations = 0;
-static int g_eq_impl = 2;  // 1: register-operand evaluation (stage_equation_item), 2: slot-based evaluation (fqs.cuh), what k_equation runs
+static int g_eq_impl = 1;  // 1: register-operand evaluation (stage_equation_item), what k_equation runs; 2: slot-based evaluation (fqs.cuh, the -DJJS_EQ_V2 build)
 static bool equation_with_rtest(int variant, int eq, const fq* pu, const fq* pv, uint8_t* pf, size_t n, size_t i, const WireField& fu, const uint32_t* cw,
                                 fq* tab) {
     bool need;
@@ -235,6 +235,26 @@ int hs_half_gcd(const uint8_t* c32, uint8_t* tau20, uint8_t* rho16, int8_t* digi
     }
     return (neg ? 1 : 0) | (odd ? 2 : 0);
 }
+// three short scalars of the var-generator equation: magnitudes (32 bytes each) and flags (bit 0/1/2: x/y/z negative, bit 3: z odd);
+// returns 0 if no vector fits the 43 windows; digits (optional, 3 x 64 signed bytes): what the equation kernel uses for x, y, -z
+int hs_lattice3(const uint8_t* u32, const uint8_t* c32, uint8_t* x32, uint8_t* y32, uint8_t* z32, int* flags, int8_t* digits) {
+    uint32_t u[8], c[8], xm[8], ym[8], zm[8];
+    memcpy(u, u32, 32);
+    memcpy(c, c32, 32);
+    bool xn, yn, zn, odd;
+    if (!lattice3_reduce(xm, ym, zm, xn, yn, zn, odd, u, c)) return 0;
+    memcpy(x32, xm, 32);
+    memcpy(y32, ym, 32);
+    memcpy(z32, zm, 32);
+    *flags = (xn ? 1 : 0) | (yn ? 2 : 0) | (zn ? 4 : 0) | (odd ? 8 : 0);
+    if (digits) {
+        memset(digits, 0, 192);
+        recode_signed16_n<6>(digits, xm, xn);
+        recode_signed16_n<6>(digits + 64, ym, yn);
+        recode_signed16_n<6>(digits + 128, zm, !zn);
+    }
+    return 1;
+}
 int hs_subgroup(const uint8_t* p32, int method) {
     ensure_ready();
     std::vector<fq> tab(36);
@@ -244,7 +264,7 @@ int hs_subgroup(const uint8_t* p32, int method) {
 void hs_verify_ext(int variant, const uint8_t* pts, const uint8_t* u32, const uint8_t* msg, size_t n, uint8_t* status, uint8_t* c_out) {
     ensure_ready();
     const int slots = variant_slots(variant);
-    std::vector<fq> pu(slots * n), pv(slots * n), tab(72);
+    std::vector<fq> pu(slots * n), pv(slots * n), tab(108);
     std::vector<uint8_t> pf(slots * n), itf(n);
     std::vector<uint32_t> cw(8 * n);
     WireField fmsg{msg, 32}, fu{u32, 32};
@@ -309,7 +329,7 @@ void hs_verify(int variant, const uint8_t* pk, const uint8_t* sig, const uint8_t
     else if (variant == VAR_DOUBLE) { f[0] = {pk, 64}; f[1] = {pk + 32, 64}; f[2] = {sig + 32, 96}; f[3] = {sig + 64, 96}; }
     else { f[0] = {pk, 64}; f[1] = {pk + 32, 64}; f[2] = {sig + 32, 64}; }
     (void)pk_stride;
-    std::vector<fq> pu(slots * n), pv(slots * n), tab(72);
+    std::vector<fq> pu(slots * n), pv(slots * n), tab(108);
     std::vector<uint8_t> pf(slots * n), itf(n);
     std::vector<uint32_t> cw(8 * n);
     for (int s = 0; s < slots; s++)

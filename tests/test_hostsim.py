@@ -173,7 +173,8 @@ def _p(a):
 @pytest.mark.parametrize("impl", [2, 1])
 @pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
 def test_pipeline_twin_on_adversarial_batches(L, vi, kind, impl):
-    """impl 2: the slot-based equation the kernel runs (csrc/fqs.cuh); impl 1: the register-operand evaluation kept for A/B builds."""
+    """impl 1: the register-operand evaluation k_equation runs (var-gen: three short scalars); impl 2: the slot-based evaluation of
+    csrc/fqs.cuh kept as a compile-time alternative (var-gen: two full-size scalars)."""
     L.hs_set_equation_impl(impl)
     gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
     ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
@@ -183,7 +184,7 @@ def test_pipeline_twin_on_adversarial_batches(L, vi, kind, impl):
     st, c = ver(pk, sig, msg)
     hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
     L.hs_verify(vi, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
-    L.hs_set_equation_impl(2)
+    L.hs_set_equation_impl(1)
     bad = np.nonzero(hst != st)[0]
     assert bad.size == 0, [(int(i), names[i], int(hst[i]), int(st[i])) for i in bad[:5]]
     assert np.array_equal(hc, c) and np.array_equal(st, exp)
@@ -226,6 +227,41 @@ def test_half_size_decomposition(L):
         assert sum(x << (4 * i) for i, x in enumerate(d[:33])) == (-tau if fl & 1 else tau)
         assert sum(x << (4 * i) for i, x in enumerate(d[33:])) == -rho
     assert odd > 0.93 * len(cs), odd
+
+
+def test_three_short_scalars(L):
+    """lattice3_reduce: x == z u and y == z c (mod r) with z != 0 and all three below 2^170, the 43 digits recompose them, a
+    vector is found for every random challenge and z is odd for nearly all of them; degenerate inputs either give a valid
+    triple or report 'none' (the kernel then evaluates the equation directly)."""
+    rng = np.random.default_rng(11)
+    r = o.R_ORDER
+    special = [0, 1, 2, r - 1, r - 2, 1 << 126, (1 << 126) - 1, (1 << 125) + 1, 1 << 249, (1 << 250) - 1, r // 2, r // 3, 1 << 84, 1 << 168]
+    cases = [(u, c) for u in special for c in special if c < (1 << 250) or c in (r - 1, r - 2, r // 2, r // 3)]
+    n_special = len(cases)
+    cases += [(int.from_bytes(rng.bytes(32), "little") % r, int.from_bytes(rng.bytes(32), "little") % (1 << 250)) for _ in range(3000)]
+    found = odd = 0
+    for k, (u, c) in enumerate(cases):
+        xb, yb, zb, fl, dig = (C.c_uint8 * 32)(), (C.c_uint8 * 32)(), (C.c_uint8 * 32)(), C.c_int(0), (C.c_int8 * 192)()
+        ok = L.hs_lattice3((C.c_uint8 * 32).from_buffer_copy(u.to_bytes(32, "little")), (C.c_uint8 * 32).from_buffer_copy(c.to_bytes(32, "little")),
+                           xb, yb, zb, C.byref(fl), dig)
+        if not ok:
+            assert k < n_special, (hex(u), hex(c))     # only degenerate inputs may come back empty
+            continue
+        f = fl.value
+        x, y, z = (int.from_bytes(bytes(b), "little") for b in (xb, yb, zb))
+        assert max(x, y, z) < (1 << 170) and z != 0, (hex(u), hex(c))
+        sx, sy, sz = (-x if f & 1 else x), (-y if f & 2 else y), (-z if f & 4 else z)
+        assert (sx - sz * u) % r == 0 and (sy - sz * c) % r == 0, (hex(u), hex(c))
+        assert bool(f & 8) == bool(z & 1)
+        d = list(dig)
+        assert all(-8 <= v <= 8 for v in d)
+        for j, want in enumerate((sx, sy, -sz)):
+            assert sum(v << (4 * i) for i, v in enumerate(d[64 * j:64 * j + 43])) == want
+            assert not any(d[64 * j + 43:64 * j + 64])
+        if k >= n_special:
+            found += 1
+            odd += (f >> 3) & 1
+    assert found == 3000 and odd > 0.99 * found, (found, odd)
 
 
 @pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
