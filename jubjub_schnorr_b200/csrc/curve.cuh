@@ -454,6 +454,27 @@ JJS_HD void varbase_mul(ext& r, const fq* tab, size_t stride, const DIGITS& digi
     r = acc;
 }
 
+// acc = 16 acc (T defined on return).  JJS_ROLL_DBL: the three doublings without T as a rolled loop over one inlined copy
+// (in place: ext_dbl_inl reads all of its input before it writes), which takes two of the four copies out of the hot loop.
+#ifndef JJS_ROLL_DBL
+#define JJS_ROLL_DBL 1
+#endif
+#if JJS_ROLL_DBL
+#define JJS_DBL4(acc, t)                                                \
+    do {                                                                \
+        _Pragma("unroll 1") for (int k_ = 0; k_ < 3; k_++) ext_dbl<false>(acc, acc); \
+        ext_dbl<true>(acc, acc);                                        \
+    } while (0)
+#else
+#define JJS_DBL4(acc, t)          \
+    do {                          \
+        ext_dbl<false>(t, acc);   \
+        ext_dbl<false>(acc, t);   \
+        ext_dbl<false>(t, acc);   \
+        ext_dbl<true>(acc, t);    \
+    } while (0)
+#endif
+
 // acc = sum_i 16^i (dA[i] * A + dB[i] * B) over N signed radix-16 digits each (Straus: the doublings are shared);
 // tabA / tabB are per-thread tables from varbase_table_build.  acc.T is defined on return.  The second addition of a
 // window is followed by a doubling, which does not read T, so it skips that product in every window but the last.
@@ -465,10 +486,7 @@ JJS_HD void straus2(ext& r, const fq* tabA, const fq* tabB, size_t stride, const
 #pragma unroll 1
     for (int i = N - 1; i >= 0; i--) {
         if (i != N - 1) {
-            ext_dbl<false>(t, acc);
-            ext_dbl<false>(acc, t);
-            ext_dbl<false>(t, acc);
-            ext_dbl<true>(acc, t);
+            JJS_DBL4(acc, t);
         }
         int da = dA[i], db = dB[i];
         pniels_load(n, tabA, stride, da < 0 ? -da : da);
@@ -492,10 +510,7 @@ JJS_HD void straus_multi(ext& r, int nb, const fq* tab, size_t stride, const int
 #pragma unroll 1
     for (int i = nd - 1; i >= 0; i--) {
         if (i != nd - 1) {
-            ext_dbl<false>(t, acc);
-            ext_dbl<false>(acc, t);
-            ext_dbl<false>(t, acc);
-            ext_dbl<true>(acc, t);
+            JJS_DBL4(acc, t);
         }
 #pragma unroll 1
         for (int b = 0; b < nb; b++) {

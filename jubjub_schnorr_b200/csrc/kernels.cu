@@ -1011,7 +1011,7 @@ inline double part_weight(const HostPart& p) {   // relative cost of one item (e
         double avg = p.n ? (double)(p.offsets[p.n] - p.offsets[0]) / (double)p.n : 0.0;
         return 1.0 + 0.75 * avg;
     }
-    return p.variant == VAR_DOUBLE ? 1.9 : (p.variant == VAR_VARGEN ? 1.45 : 1.0);
+    return p.variant == VAR_DOUBLE ? 1.9 : (p.variant == VAR_VARGEN ? 1.4 : 1.0);
 }
 
 // shards[part][device].  Large parts are split evenly (every device then carries the same share of every kind, so the

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) bench(uint32_t* out, uint32_t seed, long 
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+static int g_clock_khz = 1;
 template <int MODE>
 static void run(const char* name, double mults_per_iter, int sms, int blocks_per_sm, uint32_t* d_out, long long* d_cyc, bool last) {
     int blocks = sms * blocks_per_sm;
@@ -104,14 +105,18 @@ static void run(const char* name, double mults_per_iter, int sms, int blocks_per
     double cyc = 0; for (int i = 0; i < blocks; i++) cyc += (double)h[i]; cyc /= blocks;
     free(h);
     double ops_per_block = 256.0 * ITERS * mults_per_iter;
-    double per_clk_sm = ops_per_block * blocks_per_sm / cyc;   // all resident blocks of one SM run concurrently
     double per_sec = ops_per_block * blocks / (best * 1e-3);
+    // lanes per clock per SM from the SAME CUDA-event time as the T/s column, at the clock the device reports as its maximum
+    // (the clocks log of the run shows whether it held it).  The first version of this tool divided by the blocks' own
+    // clock64() spans instead, which over-counts when the resident blocks of an SM do not start together (102 vs 64 for IMAD).
+    double per_clk_sm = per_sec / ((double)sms * (double)g_clock_khz * 1e3);
     printf("  {\"kernel\": \"%s\", \"mult_lanes_per_clk_per_sm\": %.2f, \"mult_Tops_per_s\": %.3f, \"ms\": %.4f, \"avg_block_cycles\": %.0f}%s\n",
            name, per_clk_sm, per_sec * 1e-12, best, cyc, last ? "" : ",");
 }
 
 int main() {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    g_clock_khz = p.clockRate;
     int sms = p.multiProcessorCount, bps = 4;   // 4 x 256 threads = 32 warps per SM
     uint32_t* d_out; long long* d_cyc;
     CK(cudaMalloc(&d_out, sizeof(uint32_t) * sms * bps * 256));

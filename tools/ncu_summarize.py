@@ -34,6 +34,7 @@ def read(path):
             continue
         d = dict(zip(names, r))
         k = d["Kernel Name"].split("(")[0].split("::")[-1]
+        k = "k_equation_vargen" if k == "k_equation<1>" else k.split("<")[0]   # k_equation<0>: fixed base, <1>: var-generator
         if k not in out:
             out[k] = (d, dict(zip(names, units)))
     return out
@@ -52,7 +53,7 @@ def main():
     for f in files:
         for k, v in read(f).items():
             kernels.setdefault(k, v)
-    order = [k for k in ("k_decode", "k_challenge", "k_equation", "k_rtest", "k_agg_coeffs", "k_aggregate") if k in kernels]
+    order = [k for k in ("k_decode", "k_challenge", "k_equation", "k_equation_vargen", "k_rtest", "k_agg_coeffs", "k_aggregate") if k in kernels]
     lines = [f"# {tag} ncu summary", "",
              "ncu --set full --clock-control none --import-source on (tools/profile_round.sh); one launch per kernel after warm-up. "
              "Reports stay in gpurun_out/; the launch list of the default bench command is `" + tag + "_launches.csv`.", "",
