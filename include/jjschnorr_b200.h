@@ -190,6 +190,12 @@ int jjs_challenge_only(jjs_ctx* ctx, int variant, const uint8_t* pk, const uint8
  * out[i] = 1 / 0, or 0xff if the encoding does not decode.  Host buffers; a cross-check hook for the tests. */
 int jjs_subgroup_check(jjs_ctx* ctx, const uint8_t* points32, size_t n, int method, uint8_t* out);
 
+/* Fixed-base table self-check (a cross-check hook for the tests, like jjs_subgroup_check): the library builds its window tables
+ * for G (which = 0) and G' (which = 1) incrementally; this recomputes the n table entries named by `entries` (flat indices,
+ * window * 2^width + digit, reduced modulo the table size) from their definition digit * 2^(width * window) * B by plain
+ * double-and-add on device 0 and counts the entries that differ.  Host buffers. */
+int jjs_fb_table_check(jjs_ctx* ctx, int which, const uint32_t* entries, size_t n, uint32_t* mismatches);
+
 /* Batch key derivation + signing on device 0 of the context (used to make large
  * synthetic batches and by the tests).  For each item: pk = PublicKey::from(&sk) (reference
  * src/keys/public.rs:54-60; PublicKeyDouble / PublicKeyVarGen likewise) and sig = sk.sign(rng, msg) with the

@@ -15,7 +15,7 @@ EXPORTS = [
     "jjs_init", "jjs_destroy", "jjs_last_error", "jjs_device_count", "jjs_launch_count",
     "jjs_verify_single", "jjs_verify_double", "jjs_verify_vargen", "jjs_verify_aggregate",
     "jjs_verify_single_device", "jjs_verify_double_device", "jjs_verify_vargen_device",
-    "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect", "jjs_subgroup_check", "jjs_verify_aggregate_device", "jjs_sign_aggregate_batch", "jjs_verify_ext", "jjs_points_to_ext", "jjs_multisig_combine",
+    "jjs_challenge_only", "jjs_sign_batch", "jjs_profile_enable", "jjs_profile_collect", "jjs_subgroup_check", "jjs_fb_table_check", "jjs_verify_aggregate_device", "jjs_sign_aggregate_batch", "jjs_verify_ext", "jjs_points_to_ext", "jjs_multisig_combine",
     "jjs_verify_batch", "jjs_status_bitmap_device", "jjs_verify_batch_double", "jjs_verify_batch_vargen", "jjs_verify_batch_aggregate",
     "jjs_verify_mixed",
 ]
@@ -86,6 +86,8 @@ def lib():
     L.jjs_profile_collect.restype = C.c_int
     L.jjs_subgroup_check.argtypes = [vp, vp, sz, C.c_int, vp]
     L.jjs_subgroup_check.restype = C.c_int
+    L.jjs_fb_table_check.argtypes = [vp, C.c_int, vp, sz, vp]
+    L.jjs_fb_table_check.restype = C.c_int
     L.jjs_verify_aggregate_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
     L.jjs_verify_aggregate_device.restype = C.c_int
     L.jjs_sign_aggregate_batch.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp]

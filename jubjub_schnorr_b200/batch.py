@@ -253,6 +253,13 @@ class BatchVerifier:
         self._check(self._lib.jjs_subgroup_check(self._ctx, pts.ctypes.data, pts.shape[0], method, out.ctypes.data), "jjs_subgroup_check")
         return out
 
+    def fb_table_check(self, which, entries):
+        """Number of the given fixed-base table entries (flat indices) that differ from their definition; which: 0 G, 1 G'."""
+        idx = np.ascontiguousarray(entries, dtype=np.uint32)
+        bad = np.zeros(1, dtype=np.uint32)
+        self._check(self._lib.jjs_fb_table_check(self._ctx, int(which), idx.ctypes.data, idx.shape[0], bad.ctypes.data), "jjs_fb_table_check")
+        return int(bad[0])
+
     def sign_batch(self, variant, sk32, rnd32, msg32, gen_scalar32=None):
         """(pk bytes, sig bytes) for n items; mirrors PublicKey::from(&sk) + sk.sign(rng, msg) of the reference."""
         sk, rnd, msg = _u8(sk32, 32, "sk"), _u8(rnd32, 32, "rnd"), _u8(msg32, 32, "msg")

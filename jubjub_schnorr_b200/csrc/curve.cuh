@@ -19,10 +19,19 @@ JJS_HD void fq_load_const(fq& r, const uint32_t* c) {
 // ---------------------------------------------------------------------------------------------
 // large lookup tables living in global memory (device) or in the generated host arrays (hostsim)
 // ---------------------------------------------------------------------------------------------
+// Fixed-base window width (bits).  One mixed addition per window and no doublings, so wider windows mean fewer additions, and
+// HBM is there to be used: 21-bit windows are 12 windows x 2^21 entries x 96 B = 2.4 GB per base (G and G'), one random
+// 96-byte read per window.  Measured on B200 per 2^20 single equations: 12 bits (21 windows, 8.3 MB, L2 resident) 26.79 ms,
+// 14: 26.48, 16: 26.25, 18: 26.46 (sic), 21 (12 windows): 25.80 -- every window saved is worth its seven products and the DRAM
+// reads cost nothing visible next to the ~1 700 products of an equation.  The host twin (tests/hostsim) keeps 12 bits.
 #ifndef JJS_FB_W
+#if defined(__CUDACC__)
+#define JJS_FB_W 21
+#else
 #define JJS_FB_W 12
 #endif
-constexpr int FB_W = JJS_FB_W;                // fixed-base window width (bits): 21 windows x 4096 entries x 96 B = 8.3 MB per base, L2 resident
+#endif
+constexpr int FB_W = JJS_FB_W;
 constexpr int FB_WINDOWS = (252 + FB_W - 1) / FB_W;
 constexpr int FB_ENTRIES = 1 << FB_W;
 
@@ -559,20 +568,20 @@ JJS_HD void fixedbase_acc(ext& acc, const niels* table, const uint32_t* k) {
     }
 }
 
-// One entry of a fixed-base window table: j * 2^(FB_W w) * B as affine Niels (table construction only).
-JJS_HD void fb_table_entry(niels& out, const fq& bu, const fq& bv, int w, int j) {
+// j * 2^doublings * B in affine coordinates, j < 2^jbits (table construction only)
+JJS_HD void fb_affine_multiple(fq& u, fq& v, const fq& bu, const fq& bv, int doublings, int j, int jbits) {
     ext base, acc, t;
     pniels nb;
     ext_from_affine(base, bu, bv);
 #pragma unroll 1
-    for (int i = 0; i < w * FB_W; i++) {
+    for (int i = 0; i < doublings; i++) {
         ext_dbl<true>(t, base);
         base = t;
     }
     ext_to_pniels(nb, base);
     ext_identity(acc);
 #pragma unroll 1
-    for (int b = FB_W - 1; b >= 0; b--) {
+    for (int b = jbits - 1; b >= 0; b--) {
         ext_dbl<true>(t, acc);
         acc = t;
         if ((j >> b) & 1) {
@@ -580,15 +589,58 @@ JJS_HD void fb_table_entry(niels& out, const fq& bu, const fq& bv, int w, int j)
             acc = t;
         }
     }
-    fq zi, u, v, d2;
+    fq zi;
     fq_inv(zi, acc.Z);
     fq_mul(u, acc.X, zi);
     fq_mul(v, acc.Y, zi);
+}
+JJS_HD void niels_from_affine(niels& out, const fq& u, const fq& v) {
+    fq d2;
     fq_load_const(d2, JJS_C(EDWARDS_2D));
     fq_add(out.ypx, v, u);
     fq_sub(out.ymx, v, u);
     fq_mul(out.t2d, u, v);
     fq_mul(out.t2d, out.t2d, d2);
+}
+// One entry of a fixed-base window table: j * 2^(FB_W w) * B as affine Niels, from scratch (the definition; the device builds
+// its tables in two passes, see fb_combine_entries, and the host twin incrementally -- both are checked against this one).
+JJS_HD void fb_table_entry(niels& out, const fq& bu, const fq& bv, int w, int j) {
+    fq u, v;
+    fb_affine_multiple(u, v, bu, bv, w * FB_W, j, FB_W);
+    niels_from_affine(out, u, v);
+}
+// Two-pass construction of a window: with j = jh 2^FB_LO + jl the entry is H[jh] + S[jl] for the small tables
+// S[jl] = jl 2^(FB_W w) B (2^FB_LO affine points) and H[jh] = jh 2^(FB_W w + FB_LO) B (2^FB_HI points).  A thread combines
+// FB_BATCH consecutive entries (same jh) and shares one inversion among them (Montgomery's trick): ~50 products per entry
+// instead of the ~1 200 of fb_table_entry, which is what makes 2^21-entry windows cheap to build (12 x 2^21 entries x 2 bases
+// in well under a second).
+constexpr int FB_LO = (FB_W + 1) / 2, FB_HI = FB_W - FB_LO, FB_BATCH = 8;
+JJS_HD void fb_combine_entries(niels* out, const fq* s_u, const fq* s_v, const fq& hu, const fq& hv) {
+    ext h, p[FB_BATCH];
+    ext_from_affine(h, hu, hv);
+    fq prefix[FB_BATCH];
+#pragma unroll 1
+    for (int k = 0; k < FB_BATCH; k++) {
+        niels n;
+        niels_from_affine(n, s_u[k], s_v[k]);
+        ext_add_niels<false>(p[k], h, n);
+        if (k == 0) prefix[0] = p[0].Z;
+        else fq_mul(prefix[k], prefix[k - 1], p[k].Z);
+    }
+    fq inv;
+    fq_inv(inv, prefix[FB_BATCH - 1]);   // the addition law is complete: no Z is zero
+#pragma unroll 1
+    for (int k = FB_BATCH - 1; k >= 0; k--) {
+        fq zi, u, v;
+        if (k == 0) zi = inv;
+        else {
+            fq_mul(zi, inv, prefix[k - 1]);
+            fq_mul(inv, inv, p[k].Z);
+        }
+        fq_mul(u, p[k].X, zi);
+        fq_mul(v, p[k].Y, zi);
+        niels_from_affine(out[k], u, v);
+    }
 }
 
 // is_torsion_free by the order-8 Tate pairing: E(Fq) is cyclic of order 8 r, so an affine point P != O lies in

@@ -361,15 +361,43 @@ __global__ void __launch_bounds__(BLOCK) k_bitmap(const uint8_t* status, size_t 
     if ((threadIdx.x & 31) == 0 && i < n) words[i >> 5] = w;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_fb_table(niels* out, int which) {
+// Fixed-base tables in two passes (curve.cuh, fb_combine_entries).  Pass 1: the small tables of every window, affine points,
+// small[w][0 .. 2^FB_LO) = jl 2^(FB_W w) B  and  small[w][2^FB_LO .. 2^FB_LO + 2^FB_HI) = jh 2^(FB_W w + FB_LO) B.
+constexpr int FB_SMALL = (1 << FB_LO) + (1 << FB_HI);
+__global__ void __launch_bounds__(BLOCK) k_fb_small(fq* small_u, fq* small_v, int which) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= FB_WINDOWS * FB_ENTRIES) return;
+    if (t >= FB_WINDOWS * FB_SMALL) return;
+    fq bu, bv, u, v;
+    fq_load_const(bu, which ? JJS_C(GEN_NUMS_UV)[0] : JJS_C(GEN_UV)[0]);
+    fq_load_const(bv, which ? JJS_C(GEN_NUMS_UV)[1] : JJS_C(GEN_UV)[1]);
+    int w = t / FB_SMALL, e = t % FB_SMALL;
+    if (e < (1 << FB_LO)) fb_affine_multiple(u, v, bu, bv, w * FB_W, e, FB_LO);
+    else fb_affine_multiple(u, v, bu, bv, w * FB_W + FB_LO, e - (1 << FB_LO), FB_HI);
+    small_u[t] = u;
+    small_v[t] = v;
+}
+// Pass 2: thread t combines entries [FB_BATCH t, FB_BATCH (t + 1)) of the table (FB_BATCH divides 2^FB_LO, so they share jh).
+__global__ void __launch_bounds__(BLOCK) k_fb_combine(niels* out, const fq* small_u, const fq* small_v) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)FB_WINDOWS * FB_ENTRIES / FB_BATCH) return;
+    size_t first = t * FB_BATCH;
+    int w = (int)(first / FB_ENTRIES), j = (int)(first % FB_ENTRIES), jh = j >> FB_LO, jl = j & ((1 << FB_LO) - 1);
+    const fq* su = small_u + (size_t)w * FB_SMALL;
+    const fq* sv = small_v + (size_t)w * FB_SMALL;
+    fb_combine_entries(out + first, su + jl, sv + jl, su[(1 << FB_LO) + jh], sv[(1 << FB_LO) + jh]);
+}
+// the definition, entry by entry (jjs_fb_table_check compares a sample of the built tables with it)
+__global__ void __launch_bounds__(BLOCK) k_fb_check(const niels* table, int which, const uint32_t* entries, int n, uint32_t* mismatches) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
     fq u, v;
     fq_load_const(u, which ? JJS_C(GEN_NUMS_UV)[0] : JJS_C(GEN_UV)[0]);
     fq_load_const(v, which ? JJS_C(GEN_NUMS_UV)[1] : JJS_C(GEN_UV)[1]);
     niels e;
-    fb_table_entry(e, u, v, t / FB_ENTRIES, t % FB_ENTRIES);
-    out[t] = e;
+    uint32_t idx = entries[t] % (uint32_t)(FB_WINDOWS * FB_ENTRIES);
+    fb_table_entry(e, u, v, (int)(idx / FB_ENTRIES), (int)(idx % FB_ENTRIES));
+    const niels& g = table[idx];
+    if (!(fq_eq(e.ypx, g.ypx) && fq_eq(e.ymx, g.ymx) && fq_eq(e.t2d, g.t2d))) atomicAdd(mismatches, 1u);
 }
 
 // one thread signs one item; inputs are 32-byte little-endian scalars, outputs the reference's wire bytes.
@@ -1385,11 +1413,22 @@ int init_device(jjs_ctx* ctx, DeviceState& d) {
     const size_t fb_bytes = sizeof(niels) * FB_WINDOWS * FB_ENTRIES;
     JJS_CUDA(ctx, cudaMalloc(&d.fb_g, fb_bytes));
     JJS_CUDA(ctx, cudaMalloc(&d.fb_gn, fb_bytes));
-    k_fb_table<<<blocks_for(FB_WINDOWS * FB_ENTRIES), BLOCK, 0, d.stream>>>(d.fb_g, 0);
-    k_fb_table<<<blocks_for(FB_WINDOWS * FB_ENTRIES), BLOCK, 0, d.stream>>>(d.fb_gn, 1);
-    ctx->launches += 2;
-    JJS_CUDA(ctx, cudaGetLastError());
-    JJS_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    {
+        static_assert((1 << FB_LO) % FB_BATCH == 0, "a batch of table entries must share its high half");
+        fq *small_u = nullptr, *small_v = nullptr;
+        JJS_CUDA(ctx, cudaMalloc(&small_u, sizeof(fq) * FB_WINDOWS * FB_SMALL));
+        JJS_CUDA(ctx, cudaMalloc(&small_v, sizeof(fq) * FB_WINDOWS * FB_SMALL));
+        for (int which = 0; which < 2; which++) {
+            k_fb_small<<<blocks_for(FB_WINDOWS * FB_SMALL), BLOCK, 0, d.stream>>>(small_u, small_v, which);
+            k_fb_combine<<<blocks_for((size_t)FB_WINDOWS * FB_ENTRIES / FB_BATCH), BLOCK, 0, d.stream>>>(which ? d.fb_gn : d.fb_g, small_u, small_v);
+        }
+        ctx->launches += 4;
+        cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(d.stream);
+        cudaFree(small_u);
+        cudaFree(small_v);
+        JJS_CUDA(ctx, e1);
+        JJS_CUDA(ctx, e2);
+    }
     return ensure_tags(ctx, d, 1023);
 }
 
@@ -1598,6 +1637,25 @@ JJS_API int jjs_subgroup_check(jjs_ctx* ctx, const uint8_t* points32, size_t n, 
             ctx->launches++;
         }
     });
+}
+JJS_API int jjs_fb_table_check(jjs_ctx* ctx, int which, const uint32_t* entries, size_t n, uint32_t* mismatches) {
+    JJS_ENTER(ctx);
+    if (which < 0 || which > 1) return fail(ctx, JJS_ERR_ARGUMENT, "bad table");
+    if (!mismatches) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    *mismatches = 0;
+    if (n == 0) return JJS_SUCCESS;
+    if (!entries) return fail(ctx, JJS_ERR_ARGUMENT, "null buffer");
+    const void* srcs[1] = {entries};
+    const size_t bytes[1] = {4 * n};
+    uint32_t count = 0;
+    int rc = run_small(ctx, "fixed-base table check", 4 * n, 4, srcs, bytes, 1, &count, [&](DeviceState& d, uint8_t* in, uint8_t* o) {
+        cudaMemsetAsync(o, 0, 4, d.stream);
+        k_fb_check<<<blocks_for(n), BLOCK, 0, d.stream>>>(which ? d.fb_gn : d.fb_g, which, reinterpret_cast<const uint32_t*>(in), (int)n,
+                                                         reinterpret_cast<uint32_t*>(o));
+        ctx->launches++;
+    });
+    *mismatches = count;
+    return rc;
 }
 JJS_API int jjs_sign_aggregate_batch(jjs_ctx* ctx, const uint8_t* sk32, const uint32_t* offsets, const uint8_t* rnd32, const uint8_t* msg32, size_t n,
                                      uint8_t* pks32_out, uint8_t* sig64_out) {

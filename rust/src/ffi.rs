@@ -92,6 +92,7 @@ extern "C" {
     pub fn jjs_challenge_only(ctx: *mut jjs_ctx, variant: c_int, pk: *const u8, sig: *const u8, msg32: *const u8, n: usize,
                               c32: *mut u8) -> c_int;
     pub fn jjs_subgroup_check(ctx: *mut jjs_ctx, points32: *const u8, n: usize, method: c_int, out: *mut u8) -> c_int;
+    pub fn jjs_fb_table_check(ctx: *mut jjs_ctx, which: c_int, entries: *const u32, n: usize, mismatches: *mut u32) -> c_int;
     pub fn jjs_sign_batch(ctx: *mut jjs_ctx, variant: c_int, sk32: *const u8, rnd32: *const u8, gen_scalar32_or_null: *const u8,
                           msg32: *const u8, n: usize, pk_out: *mut u8, sig_out: *mut u8) -> c_int;
     pub fn jjs_sign_aggregate_batch(ctx: *mut jjs_ctx, sk32: *const u8, offsets: *const u32, rnd32: *const u8, msg32: *const u8,

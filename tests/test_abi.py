@@ -78,6 +78,7 @@ def test_failed_init_leaves_an_inert_context():
         lambda: lib.jjs_points_to_ext(ctx, buf, buf, n, buf),
         lambda: lib.jjs_challenge_only(ctx, 0, buf, buf, buf, n, buf),
         lambda: lib.jjs_subgroup_check(ctx, buf, n, 0, buf),
+        lambda: lib.jjs_fb_table_check(ctx, 0, buf, n, buf),
         lambda: lib.jjs_sign_batch(ctx, 0, buf, buf, None, buf, n, buf, buf),
         lambda: lib.jjs_sign_aggregate_batch(ctx, buf, off, buf, buf, n, buf, buf),
         lambda: lib.jjs_multisig_combine(ctx, buf, buf, buf, buf, off, buf, n, None, buf, None, None),

@@ -119,6 +119,19 @@ def test_ragged_and_empty(bv):
         assert st.shape == (n,) and (st == 0).all()
 
 
+def test_fixed_base_tables_match_their_definition(bv):
+    """The window tables for G and G' are built in two passes with shared inversions (csrc/curve.cuh, fb_combine_entries); a sample
+    of entries -- the first and last digit of every window, batch boundaries, random ones -- is recomputed on the GPU by plain
+    double-and-add from the definition digit * 2^(width * window) * B and must agree exactly.  (The tables are exercised end to end
+    by every signing and verification test as well; this one localises a fault.)"""
+    rng = np.random.default_rng(21)
+    size = 12 << 21   # 12 windows of 2^21 entries (the device default, JJS_FB_W = 21)
+    edges = [w * (1 << 21) + d for w in range(12) for d in (0, 1, 7, 8, 9, (1 << 11) - 1, 1 << 11, (1 << 11) + 1, (1 << 21) - 9, (1 << 21) - 8, (1 << 21) - 1)]
+    idx = np.concatenate([np.asarray(edges, dtype=np.uint32), rng.integers(0, size, size=20000, dtype=np.uint32)])
+    for which in (0, 1):
+        assert bv.fb_table_check(which, idx) == 0
+
+
 def test_subgroup_tate_equals_scalar_mul_definition(bv):
     """The production subgroup test (order-8 Tate pairing) against [r]P == identity on the GPU, over random curve
     points in every torsion coset, the torsion points themselves and undecodable strings."""

@@ -50,6 +50,17 @@ for v, kind in ((0, "single"), (1, "double"), (2, "vargen")):
         if os.path.exists(path):
             specs.append(f"{kind}:{k}:{n // 4 if False else n}:{path}")
 # the captures ran at 2^18 items: time_stages printed the units of THAT run
+# aggregate path (bench.py --workload aggregate --log2n 17): k_agg_coeffs runs one thread per signer key, k_aggregate one per item
+try:
+    import json
+    d = json.loads([l for l in open(f"{out}/{tag}_plain_agg.log") if l.startswith("{")][-1])
+    keys = (d["e2e"]["h2d_bytes_per_step"] - (1 << 17) * (64 + 32 + 4) - 4) // 32
+    for k, n in (("k_agg_coeffs", keys), ("k_aggregate", 1 << 17)):
+        path = f"{out}/{tag}_src_agg_{k}.csv"
+        if os.path.exists(path):
+            specs.append(f"aggregate:{k}:{n}:{path}")
+except Exception as e:
+    print("no aggregate units:", e)
 subprocess.check_call([sys.executable, "tools/ncu_executed.py", tag] + specs)
 PY
 rm -f $out/${tag}_src_*.csv $out/${tag}_prof_*.ncu-rep
