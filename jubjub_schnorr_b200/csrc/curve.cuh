@@ -85,7 +85,7 @@ JJS_HD void ext_dbl_inl(ext& r, const ext& p) {
     fq_add(h, a, b);   // H'
     fq_sub(e, h, e);   // E'
     fq_sub(g, a, b);   // G'
-    fq_add(f, g, c);   // F'
+    fq_add_lazy(f, g, c);   // F' < 2q: its partners in the two products below (E', G') are reduced
     fq_mul(r.X, e, f);
     fq_mul(r.Y, g, h);
     fq_mul(r.Z, f, g);
@@ -97,13 +97,13 @@ JJS_HD void ext_add_pniels_inl(ext& r, const ext& p, const pniels& q) {
     fq a, b, c, d, e, f, g, h, t;
     fq_sub(t, p.Y, p.X);
     fq_mul(a, t, q.ymx);
-    fq_add(t, p.Y, p.X);
+    fq_add_lazy(t, p.Y, p.X);   // times a reduced table entry
     fq_mul(b, t, q.ypx);
     fq_mul(c, p.T, q.t2d);
     fq_mul(d, p.Z, q.z2);
     fq_sub(e, b, a);
     fq_sub(f, d, c);
-    fq_add(g, d, c);
+    fq_add_lazy(g, d, c);       // its partners (H, F) are reduced
     fq_add(h, b, a);
     fq_mul(r.X, e, f);
     fq_mul(r.Y, g, h);
@@ -116,13 +116,13 @@ JJS_HD void ext_add_niels_inl(ext& r, const ext& p, const niels& q) {
     fq a, b, c, d, e, f, g, h, t;
     fq_sub(t, p.Y, p.X);
     fq_mul(a, t, q.ymx);
-    fq_add(t, p.Y, p.X);
+    fq_add_lazy(t, p.Y, p.X);   // times a reduced table entry
     fq_mul(b, t, q.ypx);
     fq_mul(c, p.T, q.t2d);
     fq_dbl(d, p.Z);
     fq_sub(e, b, a);
     fq_sub(f, d, c);
-    fq_add(g, d, c);
+    fq_add_lazy(g, d, c);       // its partners (H, F) are reduced
     fq_add(h, b, a);
     fq_mul(r.X, e, f);
     fq_mul(r.Y, g, h);

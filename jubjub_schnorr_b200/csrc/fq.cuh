@@ -336,6 +336,12 @@ JJS_HD uint32_t sub_q(uint32_t* r, const uint32_t* x) {
     return borrow;
 }
 
+#if !defined(__CUDA_ARCH__)
+inline bool ge_q_host(const uint32_t* x) {  // host twin only: x >= q
+    uint32_t s[8];
+    return sub_q(s, x) == 0;
+}
+#endif
 // r = x + (q & mask) over 8 limbs (mask is 0 or 0xffffffff); carry out dropped.
 // Device: the eight additions are PREDICATED on the mask instead of adding a masked copy of q -- five instructions fewer
 // in the tail of every product, squaring and subtraction (-DJJS_PRED_ADDQ=0 restores the masked form).
@@ -653,6 +659,28 @@ JJS_HD void fq_add(fq& r, const fq& a, const fq& b) {
     uint32_t borrow = sub_q(s, v);
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = borrow ? v[i] : s[i];
+}
+// a + b WITHOUT the reduction: the sum of two reduced elements is below 2q < 2^256 and may be used as ONE operand of a
+// product whose other operand is reduced (a b < 2 q^2 < q 2^256 is all the Montgomery reduction needs; its result is fully
+// reduced again).  Never as an operand of a squaring, an addition or a comparison.  Saves the 17 instructions of the
+// conditional subtraction (-DJJS_LAZY_ADD=0: same as fq_add).
+#ifndef JJS_LAZY_ADD
+#define JJS_LAZY_ADD 1
+#endif
+JJS_HD void fq_add_lazy(fq& r, const fq& a, const fq& b) {
+#if JJS_LAZY_ADD
+    uint32_t v[8];
+    uint32_t c = add8(v, a.l, b.l);
+#if !defined(__CUDA_ARCH__)
+    if (c != 0 || ge_q_host(a.l) || ge_q_host(b.l)) jjs_host_bound_violation();   // the twin checks the contract
+#else
+    (void)c;
+#endif
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = v[i];
+#else
+    fq_add(r, a, b);
+#endif
 }
 JJS_HD void fq_sub(fq& r, const fq& a, const fq& b) {
     uint32_t v[8];

@@ -61,6 +61,33 @@ JJS_HD void fr_mul_short(uint32_t* out, const uint32_t* a4, const uint32_t* b8) 
 #pragma unroll
     for (int i = 0; i < 8; i++) out[i] = rem[i];
 }
+// The same for a < 2^160 (five limbs): x = a b < 2^412,  q = ((x >> 248) * floor(2^412 / r)) >> 164.  Used where the second
+// vector of the half-size decomposition feeds the three-scalar reduction (its rho can exceed 128 bits by a few).
+JJS_HD void fr_mul_160(uint32_t* out, const uint32_t* a5, const uint32_t* b8) {
+    constexpr uint32_t MU[6] = {0x01b7c721u, 0x83f0476au, 0x1c5aee5bu, 0xff6f1bbeu, 0x1aa84a76u, 0x1u};  // floor(2^412 / r)
+    uint32_t a[8], x[16], x1[8], mu[8], t[16], q[8], ord[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = i < 5 ? a5[i] : 0u; mu[i] = i < 6 ? MU[i] : 0u; ord[i] = JJS_C(R_ORDER)[i]; }
+    mul_wide(x, a, b8);
+    // x1 = x >> 248 (248 = 7 * 32 + 24): six limbs
+#pragma unroll
+    for (int i = 0; i < 8; i++) x1[i] = i < 6 ? ((x[7 + i] >> 24) | (x[8 + i] << 8)) : 0u;
+    mul_wide(t, x1, mu);
+    // q = t >> 164 (164 = 5 * 32 + 4): six limbs
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = i < 6 ? ((t[5 + i] >> 4) | (t[6 + i] << 28)) : 0u;
+    mul_wide(t, q, ord);
+    uint32_t rem[8], sv[8];
+    sub8(rem, x, t);   // the true value is below 3 r < 2^254
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        uint32_t borrow = sub8(sv, rem, ord);
+#pragma unroll
+        for (int i = 0; i < 8; i++) rem[i] = borrow ? rem[i] : sv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = rem[i];
+}
 JJS_HD void fr_sub(uint32_t* out, const uint32_t* a, const uint32_t* b) {  // a, b < r
     uint32_t d[8], ord[8], e[8];
 #pragma unroll
@@ -151,18 +178,6 @@ JJS_HD void half_gcd_core(uint32_t* a, uint32_t* b, uint32_t* ta, uint32_t* tb, 
         neg = !neg;
     }
 }
-JJS_HD void half_gcd(uint32_t* tau5, uint32_t* rho4, bool& rho_neg, bool& rho_odd, const uint32_t* c8) {
-    uint32_t a[8], b[8], ta[4], tb[4];
-    bool neg;
-    half_gcd_core(a, b, ta, tb, neg, c8);
-    bool prev = !(tb[0] & 1u) && (ta[0] & 1u) && (a[7] | a[6] | a[5]) == 0u && a[4] < 4u;
-#pragma unroll
-    for (int i = 0; i < 4; i++) { tau5[i] = prev ? a[i] : b[i]; rho4[i] = prev ? ta[i] : tb[i]; }
-    tau5[4] = prev ? a[4] : 0u;
-    rho_neg = prev ? !neg : neg;
-    rho_odd = (rho4[0] & 1u) != 0u;
-}
-
 // ---- three short scalars for an equation with two variable bases and a variable generator ---------------------------------
 // u*Gen + c*PK == R has no fixed base, so the half-size trick above leaves a full-size multiplier on Gen.  Multiplying the
 // equation by any z != 0 (mod r) gives the equivalent check  x*Gen + y*PK - z*R == O  with  x == z u,  y == z c  (mod r);
@@ -279,21 +294,6 @@ JJS_HD void lattice3_comb(s256& r, const double* t, const s256& o0, const s256& 
     s256_submul(r, o1, -(int32_t)t[1], 0);
     s256_submul(r, o2, -(int32_t)t[2], 0);
 }
-// takes the vector (x, y, z) if it fits the windows, has z != 0 and (when asked) an odd z
-JJS_HD bool lattice3_pick(const s256* V, bool want_odd, uint32_t* xm, uint32_t* ym, uint32_t* zm, bool& xneg, bool& yneg, bool& zneg) {
-    uint32_t nz = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) nz |= V[2].l[i];
-    if (nz == 0u || (want_odd && !(V[2].l[0] & 1u))) return false;
-    if (!(s256_fits_170(V[0]) && s256_fits_170(V[1]) && s256_fits_170(V[2]))) return false;
-    s256_abs(xm, V[0]);
-    s256_abs(ym, V[1]);
-    s256_abs(zm, V[2]);
-    xneg = s256_is_neg(V[0]);
-    yneg = s256_is_neg(V[1]);
-    zneg = s256_is_neg(V[2]);
-    return true;
-}
 constexpr int LATTICE3_MAX_ROUNDS = 16, LATTICE3_INNER = 10;
 constexpr double LATTICE3_CAP = 4194304.0;   // 2^22: bound on the entries of a round's transformation (and on every quotient)
 constexpr int LATTICE3_WINDOWS = 43;         // signed radix-16 digits of a magnitude below 2^170
@@ -324,6 +324,153 @@ JJS_HD bool lattice_any(bool p) {
     return p;
 #endif
 }
+// ---- the half-size decomposition, warp-uniform ------------------------------------------------------------------------------
+// The two shortest vectors (tau, rho) of the lattice tau == rho c (mod r), i.e. a Gauss-reduced basis, by the same scheme as
+// lattice3_reduce below (Lehmer-style rounds on doubles with an exact update per round, control flow independent of the data,
+// a warp vote per round), started from (r, 0) and (c, 1).  Nearest-integer quotients make this the centred Euclidean
+// algorithm: ~51 steps for a 250-bit challenge, 6-7 rounds.  It replaces the classical sequence of half_gcd_core above in the
+// kernels (0.7 ms per 2^20 equations there, with every lane of a warp waiting for the slowest); the shortest vector is below
+// 2^127 in both coordinates, the second one below 2^130 in all but 1 % of the cases, and one of the two has an odd rho
+// (their determinant is +-r, which is odd).
+constexpr int HGCD_MAX_ROUNDS = 24, HGCD_INNER = 14;
+JJS_HD void half_gcd_vectors(s256 (&E)[2][2], const uint32_t* c8) {   // rows (tau, rho), E[0] the shorter on return
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        E[0][0].l[i] = c8[i];
+        E[0][1].l[i] = i == 0 ? 1u : 0u;
+        E[1][0].l[i] = JJS_C(R_ORDER)[i];
+        E[1][1].l[i] = 0u;
+    }
+    bool converged = false;
+#pragma unroll 1
+    for (int round = 0; round < HGCD_MAX_ROUNDS && lattice_any(!converged); round++) {
+        double ad[2], bd[2], at[2], bt[2], an, bn;
+        ad[0] = s256_to_double(E[0][0]); ad[1] = s256_to_double(E[0][1]);
+        bd[0] = s256_to_double(E[1][0]); bd[1] = s256_to_double(E[1][1]);
+        an = ad[0] * ad[0] + ad[1] * ad[1];
+        bn = bd[0] * bd[0] + bd[1] * bd[1];
+        {   // a quotient of 2^20 or more against the first vector (tiny challenges; updates the cap kept out of a round) is applied
+            // exactly, 31 bits at a time.  E[0] is the shorter vector here except before the first round, where it is (c, 1).
+            double ratio = (ad[0] * bd[0] + ad[1] * bd[1]) * lattice_rcp(an);
+            bool big = fabs(ratio) >= 1048576.0 && an <= bn;
+            if (lattice_any(big)) {
+                int32_t k;
+                int sh;
+                lattice_digit(k, sh, big ? ratio : 0.0);
+                s256_submul(E[1][0], E[0][0], k, sh);
+                s256_submul(E[1][1], E[0][1], k, sh);
+                bd[0] = s256_to_double(E[1][0]);
+                bd[1] = s256_to_double(E[1][1]);
+                bn = bd[0] * bd[0] + bd[1] * bd[1];
+            }
+        }
+        at[0] = 1.0; at[1] = 0.0;
+        bt[0] = 0.0; bt[1] = 1.0;
+#pragma unroll 1
+        for (int it = 0; it <= HGCD_INNER; it++) {
+            bool sw = an > bn;   // A: the shorter
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                double x = ad[j], y = bd[j];
+                ad[j] = sw ? y : x;
+                bd[j] = sw ? x : y;
+                x = at[j], y = bt[j];
+                at[j] = sw ? y : x;
+                bt[j] = sw ? x : y;
+            }
+            { double x = an, y = bn; an = sw ? y : x; bn = sw ? x : y; }
+            if (it == HGCD_INNER) break;   // the last pass only orders the pair
+            double ra = (ad[0] * bd[0] + ad[1] * bd[1]) * lattice_rcp(an);
+            bool want = fabs(ra) > 0.500001;
+            double k = want ? lattice_clamp(rint(ra)) : 0.0;
+            double t0 = bt[0] - k * at[0], t1 = bt[1] - k * at[1];
+            k = (fabs(t0) <= LATTICE3_CAP && fabs(t1) <= LATTICE3_CAP) ? k : 0.0;
+            bt[0] -= k * at[0]; bt[1] -= k * at[1];
+            bd[0] -= k * ad[0]; bd[1] -= k * ad[1];
+            bn = bd[0] * bd[0] + bd[1] * bd[1];
+            converged = converged || !want;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            s256 o0 = E[0][k], o1 = E[1][k], z;
+#pragma unroll
+            for (int i = 0; i < 8; i++) z.l[i] = 0;
+            double ta3[3] = {at[0], at[1], 0.0}, tb3[3] = {bt[0], bt[1], 0.0};
+            lattice3_comb(E[0][k], ta3, o0, o1, z);
+            lattice3_comb(E[1][k], tb3, o0, o1, z);
+        }
+    }
+}
+// magnitude below 2^bits
+JJS_HD bool s256_fits(const s256& a, int bits) {
+    uint32_t m[8];
+    s256_abs(m, a);
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int lo = 32 * i;
+        if (lo >= bits) ok = ok && m[i] == 0u;
+        else if (lo + 32 > bits) ok = ok && (m[i] >> (bits - lo)) == 0u;
+    }
+    return ok;
+}
+// For c < r returns tau < 2^130 (5 limbs) and rho != 0, |rho| < 2^128 (4 limbs), with  tau == rho * c (mod r),
+// rho = rho_neg ? -|rho| : |rho|  (Antipa, Brown, Gallant, Lambert, Struik, Vanstone: "Accelerated verification of ECDSA
+// signatures").  Then, for points of the prime-order subgroup,  u*G + c*PK == R   <=>   (rho*u)*G + tau*PK - rho*R == O,  which
+// needs ~126-bit multipliers for the two variable bases.  Of the two reduced vectors the shorter one is taken if its rho is odd,
+// else the other one if it fits; an odd rho is what lets the equation kernel skip the subgroup test of R (verify_core.cuh,
+// stage_equation): rho_odd reports whether one was found (98 % of the challenges).
+JJS_HD void half_gcd_classical(uint32_t* tau5, uint32_t* rho4, bool& rho_neg, bool& rho_odd, const uint32_t* c8) {
+    uint32_t a[8], b[8], ta[4], tb[4];
+    bool neg;
+    half_gcd_core(a, b, ta, tb, neg, c8);
+    bool prev = !(tb[0] & 1u) && (ta[0] & 1u) && (a[7] | a[6] | a[5]) == 0u && a[4] < 4u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { tau5[i] = prev ? a[i] : b[i]; rho4[i] = prev ? ta[i] : tb[i]; }
+    tau5[4] = prev ? a[4] : 0u;
+    rho_neg = prev ? !neg : neg;
+    rho_odd = (rho4[0] & 1u) != 0u;
+}
+JJS_HD void half_gcd(uint32_t* tau5, uint32_t* rho4, bool& rho_neg, bool& rho_odd, const uint32_t* c8) {
+    s256 E[2][2];
+    half_gcd_vectors(E, c8);
+    if (!(s256_fits(E[0][0], 130) && s256_fits(E[0][1], 128))) {
+        // the reduction did not finish within its round cap (not seen; the floating-point steering gives no guarantee): the
+        // classical sequence, which always does
+        half_gcd_classical(tau5, rho4, rho_neg, rho_odd, c8);
+        return;
+    }
+    bool odd0 = (E[0][1].l[0] & 1u) != 0u;
+    bool use1 = !odd0 && (E[1][1].l[0] & 1u) != 0u && s256_fits(E[1][0], 130) && s256_fits(E[1][1], 128);
+    uint32_t t[8], rr[8];
+    s256 T, Rr;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { T.l[i] = use1 ? E[1][0].l[i] : E[0][0].l[i]; Rr.l[i] = use1 ? E[1][1].l[i] : E[0][1].l[i]; }
+    s256_abs(t, T);
+    s256_abs(rr, Rr);
+#pragma unroll
+    for (int i = 0; i < 5; i++) tau5[i] = t[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) rho4[i] = rr[i];
+    rho_neg = s256_is_neg(T) != s256_is_neg(Rr);   // tau is returned as a magnitude: the sign moves to rho
+    rho_odd = (rho4[0] & 1u) != 0u;
+}
+
+// takes the vector (x, y, z) if it fits the windows, has z != 0 and (when asked) an odd z
+JJS_HD bool lattice3_pick(const s256* V, bool want_odd, uint32_t* xm, uint32_t* ym, uint32_t* zm, bool& xneg, bool& yneg, bool& zneg) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nz |= V[2].l[i];
+    if (nz == 0u || (want_odd && !(V[2].l[0] & 1u))) return false;
+    if (!(s256_fits_170(V[0]) && s256_fits_170(V[1]) && s256_fits_170(V[2]))) return false;
+    s256_abs(xm, V[0]);
+    s256_abs(ym, V[1]);
+    s256_abs(zm, V[2]);
+    xneg = s256_is_neg(V[0]);
+    yneg = s256_is_neg(V[1]);
+    zneg = s256_is_neg(V[2]);
+    return true;
+}
 // On success: |x|, |y|, |z| < 2^170 as magnitudes (six limbs used) with their signs, z != 0, x == z u and y == z c (mod r);
 // z_odd tells whether z is odd (preferred: see verify_core.cuh, stage_equation).  Returns false if no basis vector fits.
 //
@@ -343,18 +490,19 @@ JJS_HD bool lattice3_reduce(uint32_t* xm, uint32_t* ym, uint32_t* zm, bool& xneg
                             const uint32_t* c8) {
     s256 E[3][3];   // rows: basis vectors (x, y, z)
     {
-        uint32_t a[8], b[8], ta[4], tb[4], m[8];
-        bool neg;
-        half_gcd_core(a, b, ta, tb, neg, c8);
-        // (rho1 u, tau1, rho1) with rho1 = neg ? ta : -ta, tau1 = a;  (rho2 u, tau2, rho2) with rho2 = neg ? -tb : tb, tau2 = b
-        fr_mul_short(m, ta, u8);
+        // (rho_i u mod r, tau_i, rho_i) for the two reduced vectors of the half-size decomposition, and (r, 0, 0)
+        s256 H[2][2];
+        half_gcd_vectors(H, c8);
+        if (!s256_fits(H[0][1], 160) || !s256_fits(H[1][1], 160)) return false;   // degenerate challenges (c tiny): direct evaluation
 #pragma unroll
-        for (int i = 0; i < 8; i++) { E[0][0].l[i] = m[i]; E[0][1].l[i] = a[i]; E[0][2].l[i] = i < 4 ? ta[i] : 0u; }
-        if (!neg) { s256_negate(E[0][0]); s256_negate(E[0][2]); }
-        fr_mul_short(m, tb, u8);
+        for (int v = 0; v < 2; v++) {
+            uint32_t rm[8], m[8];
+            s256_abs(rm, H[v][1]);
+            fr_mul_160(m, rm, u8);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { E[1][0].l[i] = m[i]; E[1][1].l[i] = b[i]; E[1][2].l[i] = i < 4 ? tb[i] : 0u; }
-        if (neg) { s256_negate(E[1][0]); s256_negate(E[1][2]); }
+            for (int i = 0; i < 8; i++) { E[v][0].l[i] = m[i]; E[v][1].l[i] = H[v][0].l[i]; E[v][2].l[i] = H[v][1].l[i]; }
+            if (s256_is_neg(H[v][1])) s256_negate(E[v][0]);
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) { E[2][0].l[i] = JJS_C(R_ORDER)[i]; E[2][1].l[i] = 0; E[2][2].l[i] = 0; }
     }

@@ -121,6 +121,7 @@ void hs_redc(const uint32_t* t16, uint32_t* r8) { redc(r8, t16); }
 void hs_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { fq x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fq_mul(z, x, y); memcpy(r, z.l, 32); }
 void hs_fq_mul_fp(const uint32_t* a, const uint32_t* b, uint32_t* r) { fq x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fq_mul_fp_inl(z, x, y); memcpy(r, z.l, 32); }
 void hs_fr_mul_short(const uint32_t* a4, const uint32_t* b8, uint32_t* r) { fr_mul_short(r, a4, b8); }
+void hs_fr_mul_160(const uint32_t* a5, const uint32_t* b8, uint32_t* r) { fr_mul_160(r, a5, b8); }
 void hs_fr_mul(const uint32_t* a8, const uint32_t* b8, uint32_t* r) { fr_mul(r, a8, b8); }
 void hs_fq_sqr(const uint32_t* a, uint32_t* r) { fq x, z; memcpy(x.l, a, 32); fq_sqr(z, x); memcpy(r, z.l, 32); }
 void hs_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { fq x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32); fq_add(z, x, y); memcpy(r, z.l, 32); }

@@ -200,6 +200,9 @@ def test_scalar_products_mod_r(L):
     for a, b in cases:
         L.hs_fr_mul_short(arr(a, 4), arr(b), out)
         assert val(out) == a * b % r, (hex(a), hex(b))
+    for a, b in [(0, 0), ((1 << 160) - 1, r - 1), (1 << 159, r - 1), (1, r - 1)] + [(rnd.getrandbits(160), rnd.randrange(r)) for _ in range(3000)]:
+        L.hs_fr_mul_160(arr(a, 5), arr(b), out)
+        assert val(out) == a * b % r, (hex(a), hex(b))
     for _ in range(200):
         a, b = rnd.randrange(r), rnd.randrange(r)
         L.hs_fr_mul(arr(a), arr(b), out)
@@ -217,7 +220,7 @@ def test_half_size_decomposition(L):
         tau_b, rho_b, dig = (C.c_uint8 * 20)(), (C.c_uint8 * 16)(), (C.c_int8 * 66)()
         fl = L.hs_half_gcd((C.c_uint8 * 32).from_buffer_copy(c.to_bytes(32, "little")), tau_b, rho_b, dig)
         tau, rho = int.from_bytes(bytes(tau_b), "little"), int.from_bytes(bytes(rho_b), "little")
-        assert 0 < rho < (1 << 126) and tau < (1 << 130), hex(c)
+        assert 0 < rho < (1 << 128) and tau < (1 << 130), hex(c)
         srho = -rho if fl & 1 else rho
         assert (srho * c - tau) % o.R_ORDER == 0, hex(c)
         assert bool(fl & 2) == bool(rho & 1)
