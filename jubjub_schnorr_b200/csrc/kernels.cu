@@ -47,10 +47,19 @@ namespace {
 #endif
 constexpr int BLOCK = JJS_BLOCK;
 #ifndef JJS_EQ_MINBLOCKS
-#define JJS_EQ_MINBLOCKS 3
+#define JJS_EQ_MINBLOCKS 4    // fixed-base equation kernel: 4 resident CTAs of 128 threads (128 registers, a few spills) beat 3 by 4 %
+#endif
+#ifndef JJS_EQ1_MINBLOCKS
+#define JJS_EQ1_MINBLOCKS 4   // var-generator equation kernel
+#endif
+#ifndef JJS_AGG_MINBLOCKS
+#define JJS_AGG_MINBLOCKS 4   // key-aggregation kernel (-1.9 % against 3)
 #endif
 #ifndef JJS_DEC_MINBLOCKS
-#define JJS_DEC_MINBLOCKS 4
+#define JJS_DEC_MINBLOCKS 8   // decode and deferred-test kernels: 4 -> 12.62 ms per 2^21 points, 6 -> 12.49, 8 -> 12.41
+#endif
+#ifndef JJS_HASH_MINBLOCKS
+#define JJS_HASH_MINBLOCKS 6  // hash kernels: 4 -> 12.78 ms per 2^20 challenges, 6 -> 12.66, 7 -> 12.92, 8 -> 13.06
 #endif
 #ifndef JJS_EQ_PERSISTENT
 #define JJS_EQ_PERSISTENT 0   // measured (gpurun_out/ab2.log): -22 % DRAM reads but +6 % time; off
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(BLOCK) k_agg_scatter(const uint32_t* offsets, 
 // one thread hashes the delinearisation coefficient of ONE signer key (sorted key order: the threads of a warp hash transcripts of
 // one length).  Per key rather than per item: an item with n signers costs n hashes of 2 + 2 n elements, and spread over n
 // threads that work no longer depends on the signer count of the neighbouring items.
-__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_agg_coeffs(const fq* keys_u, const fq* keys_v, const uint8_t* kflags,
+__global__ void __launch_bounds__(BLOCK, JJS_HASH_MINBLOCKS) k_agg_coeffs(const fq* keys_u, const fq* keys_v, const uint8_t* kflags,
                                                                           const uint32_t* offsets, const uint32_t* kmap, const uint32_t* kitem,
                                                                           uint32_t key_base, size_t n_keys, uint32_t* d_words, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_agg_coeffs(const f
 
 // one thread folds the signer keys of one item into its aggregate key (slot 0 of the single-variant point arrays)
 // `order` lists the items sorted by signer count, so the lanes of a warp loop over the same number of signers
-__global__ void __launch_bounds__(BLOCK) k_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, const uint32_t* offsets,
+__global__ void __launch_bounds__(BLOCK, JJS_AGG_MINBLOCKS) k_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, const uint32_t* offsets,
                                                      const uint32_t* order, uint32_t key_base, size_t n, fq* pts_u, fq* pts_v, uint8_t* pflags,
                                                      uint8_t* agg_out, fq* tab, size_t stride, uint32_t* d_words, Tables T) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(BLOCK) k_work_list(int variant, const uint8_t*
 }
 
 // thread t < *count hashes the challenge of item list[t]
-__global__ void __launch_bounds__(BLOCK, JJS_DEC_MINBLOCKS) k_challenge(int variant, const fq* pts_u, const fq* pts_v, size_t n, WireField msg,
+__global__ void __launch_bounds__(BLOCK, JJS_HASH_MINBLOCKS) k_challenge(int variant, const fq* pts_u, const fq* pts_v, size_t n, WireField msg,
                                                                          const uint32_t* list, const uint32_t* count, uint32_t* cwords) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *count) return;
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(BLOCK) k_subgroup_check(WireField pts, size_t 
 // membership the equation did not establish are appended to `rlist` (indices into the point arrays) for k_rtest.
 // (instantiated per kind of equation: MODE 0 fixed base -- single, double -- and MODE 1 variable base -- var-gen)
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK, JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n,
+__global__ void __launch_bounds__(BLOCK, MODE ? JJS_EQ1_MINBLOCKS : JJS_EQ_MINBLOCKS) k_equation(int variant, const fq* pts_u, const fq* pts_v, uint8_t* pflags, size_t n,
                                                     size_t first, size_t count, const uint32_t* list, const uint32_t* lcount, WireField usc,
                                                     const uint32_t* cwords, uint8_t* eqflags, fq* tab, size_t stride, Tables T,
                                                     uint32_t* rlist, uint32_t* rcount) {
