@@ -586,7 +586,13 @@ inline Region region_of(const DeviceState& d, size_t first_item, size_t cap, int
                   half & 1};
 }
 constexpr size_t SUB_ITEMS = CHUNK_ITEMS / 2;      // items per scratch half
-constexpr size_t SUB_CHUNK = size_t(1) << 18;      // items per sub-chunk of an overlapped batch
+#ifndef JJS_SUB_CHUNK_LOG2
+#define JJS_SUB_CHUNK_LOG2 19   // 2^18: 20.86 M/s device-resident on 2^20 singles, 2^19: 21.19 (fewer partially filled waves)
+#endif
+#ifndef JJS_FIRST_SLICE_LOG2
+#define JJS_FIRST_SLICE_LOG2 17  // first slice of a host-buffer shard: short, so that compute starts while the rest is still being copied
+#endif
+constexpr size_t SUB_CHUNK = size_t(1) << JJS_SUB_CHUNK_LOG2;      // items per sub-chunk of an overlapped batch (<= SUB_ITEMS)
 inline Region region_whole(const DeviceState& d) { return region_of(d, 0, CHUNK_ITEMS, 0); }
 inline Region region_half(const DeviceState& d, size_t j) { return region_of(d, (j & 1) * SUB_ITEMS, SUB_ITEMS, (int)(j & 1)); }
 
@@ -1161,7 +1167,7 @@ int device_job(jjs_ctx* ctx, size_t k, const std::vector<HostPart>& parts, const
         // Pipeline slices: slice j + 1 is copied in on the copy stream while slice j is being verified (the kernels of one
         // slice run far longer than its copy); the first slice of a device is short so that compute starts early.
         for (size_t off = 0; off < m; j++) {
-            const size_t want = j == 0 ? SUB_CHUNK / 4 : SUB_CHUNK;
+            const size_t want = j == 0 ? (size_t(1) << JJS_FIRST_SLICE_LOG2) : SUB_CHUNK;
             size_t cnt = m - off < want ? m - off : want;
             cudaStream_t cs = serial ? d.stream : d.sub[j & 1];
             Region R = region_half(d, j);
