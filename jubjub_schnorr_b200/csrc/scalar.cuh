@@ -486,8 +486,17 @@ JJS_HD bool lattice3_pick(const s256* V, bool want_odd, uint32_t* xm, uint32_t* 
 // per-lane rounds cost 8.3 ms per 2^20 equations; this one 1.5 ms, plus 0.7 ms for the half-gcd).  Taking both steps of an
 // iteration from the same state (half the dependency chain, 20 % more iterations) measured no faster; neither did replacing
 // the IEEE divisions.  Model: tools/lattice3_model.py (4-6 rounds per challenge).
+#if !defined(__CUDA_ARCH__)
+inline bool& lattice3_host_force_none() {   // host twin only: lets a test drive the callers' fallback (no vector found)
+    static bool force = false;
+    return force;
+}
+#endif
 JJS_HD bool lattice3_reduce(uint32_t* xm, uint32_t* ym, uint32_t* zm, bool& xneg, bool& yneg, bool& zneg, bool& z_odd, const uint32_t* u8,
                             const uint32_t* c8) {
+#if !defined(__CUDA_ARCH__)
+    if (lattice3_host_force_none()) return false;
+#endif
     s256 E[3][3];   // rows: basis vectors (x, y, z)
     {
         // (rho_i u mod r, tau_i, rho_i) for the two reduced vectors of the half-size decomposition, and (r, 0, 0)

@@ -112,6 +112,7 @@ static bool equation_with_rtest(int variant, int eq, const fq* pu, const fq* pv,
 
 extern "C" {
 void hs_set_equation_impl(int impl) { g_eq_impl = impl; }
+void hs_force_vargen_fallback(int on) { lattice3_host_force_none() = on != 0; }
 void hs_safe_tag(uint32_t n_absorb, uint32_t* out8) { safe_tag_mont(out8, n_absorb); }
 // counters of the deferred subgroup tests since the last call (equations evaluated, tests run)
 void hs_rtest_counters(int* equations, int* rtests) { *equations = g_equations; *rtests = g_rtests; g_equations = g_rtests = 0; }

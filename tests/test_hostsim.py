@@ -190,6 +190,22 @@ def test_pipeline_twin_on_adversarial_batches(L, vi, kind, impl):
     assert np.array_equal(hc, c) and np.array_equal(st, exp)
 
 
+def test_vargen_fallback_when_no_short_vector_is_found(L):
+    """The var-generator equation falls back to the two-table evaluation when the lattice reduction reports no vector that fits
+    its windows (unreachable with hash outputs, so the twin forces it): same statuses and challenges."""
+    n = 96
+    pk, sig, msg = co.gen_vargen(0xB200, n)
+    pk, sig, msg, exp, names = adv.make_adversarial("vargen", pk, sig, msg, seed=9, frac=0.5)
+    st, c = co.verify_vargen(pk, sig, msg)
+    hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
+    L.hs_force_vargen_fallback(1)
+    try:
+        L.hs_verify(2, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
+    finally:
+        L.hs_force_vargen_fallback(0)
+    assert np.array_equal(hst, st) and np.array_equal(hc, c) and np.array_equal(st, exp)
+
+
 def test_scalar_products_mod_r(L):
     """rho * u mod r by Barrett reduction (rho < 2^128) and the general bit-serial product, against big integers."""
     rnd = random.Random(9)

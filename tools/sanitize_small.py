@@ -22,6 +22,8 @@ with BatchVerifier([0]) as bv:
     assert np.array_equal(bv.verify_ext(0, pts, u, msg), exp)
     bv.subgroup_check(pks[:64], 0)
     bv.subgroup_check(pks[:64], 1)
+    assert bv.fb_table_check(0, np.arange(0, 12 << 21, 99991, dtype=np.uint32)) == 0
+    assert bv.fb_table_check(1, np.arange(5, 12 << 21, 199999, dtype=np.uint32)) == 0
     # a multisig session built from the aggregate batch keys (shares are garbage: exercises the failing path)
     K = int(off[8])
     st, bad, sg, ok = bv.multisig_combine(pks[:K], pks[:K], pks[:K], np.zeros((K, 32), np.uint8), off[:9], msg[:8])
