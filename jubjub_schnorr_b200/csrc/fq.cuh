@@ -374,27 +374,6 @@ JJS_HD void add_q_masked(uint32_t* r, const uint32_t* x, uint32_t mask) {
     add8(r, x, y);
 #endif
 }
-// r = x + q over 8 limbs, carry out dropped (q limbs are immediates)
-JJS_HD void add_q(uint32_t* r, const uint32_t* x) {
-#if defined(__CUDA_ARCH__)
-    asm("add.cc.u32 %0, %8, 0x00000001;\n\t"
-        "addc.cc.u32 %1, %9, 0xffffffff;\n\t"
-        "addc.cc.u32 %2, %10, 0xfffe5bfe;\n\t"
-        "addc.cc.u32 %3, %11, 0x53bda402;\n\t"
-        "addc.cc.u32 %4, %12, 0x09a1d805;\n\t"
-        "addc.cc.u32 %5, %13, 0x3339d808;\n\t"
-        "addc.cc.u32 %6, %14, 0x299d7d48;\n\t"
-        "addc.u32 %7, %15, 0x73eda753;"
-        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
-        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
-#else
-    uint32_t y[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) y[i] = q_limb(i);
-    add8(r, x, y);
-#endif
-}
-
 // (ev, od) split representation of a multi-limb value:  V = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1)).  A reduction step
 // expects ev[0] == 0 (its low limb was cancelled by the previous step; for the first step the caller presents T shifted up
 // by one limb), shifts V right by 32 bits and appends `inject` as the new top limb.
@@ -576,18 +555,15 @@ JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     add_q_masked(r, d, borrow);
 }
 
-// r == v / 2^32 (mod q) for a 9-limb v < 2^20 * q (one Montgomery step; used after the small-integer linear maps of the hash).
-// JJS_REDC_ONE_LAZY (default): the result is only ALMOST reduced, 0 <= r < q + 2^244.  With e0 the quotient digit,
-// (v + e0 qbar) / 2^32 = r0 + e0 2^224 with r0 = (v - e0 q) / 2^32 in (-q, 2^244); instead of taking e0 2^224 off and adding q
-// back on a borrow (which is the case all but once in 2^11 times) q is added unconditionally: r = r0 + q in (0, q + 2^244).
-// That is one 8-limb addition of constants in place of a subtraction, a mask and an addition (24 instructions per lane and
-// round of the permutation).  Every consumer takes such a value: the multiplier and the squarer need a b < q 2^256 (and
-// return fully reduced results), the next linear layer only uses the limbs as 32-bit integers and keeps its bound
-// (v < 2^18.1 (q + 2^244)), and the permutation ends with a product per lane (HADES_UNSCALE), so nothing unreduced
-// leaves it.  The twin checks the range.
-#ifndef JJS_REDC_ONE_LAZY
-#define JJS_REDC_ONE_LAZY 1
-#endif
+// One Montgomery step after the small-integer linear maps of the hash, without any correction: for a 9-limb
+//     v' = v + q 2^32,   v < 2^20 q   (the caller's constants carry the q 2^32: HADES_FOLDED_ARK is emitted that way)
+// returns r == v / 2^32 (mod q) with 0 < r < q + 2^244 -- ALMOST reduced.  With e0 the quotient digit (it only depends on the low
+// limb, which q 2^32 does not touch), (v' + e0 qbar) / 2^32 = r0 + q + e0 2^224 with r0 = (v - e0 q) / 2^32 in (-q, 2^244), so
+// taking e0 off limb 7 (mod 2^256) leaves r = r0 + q in (0, q + 2^244).  The subtract-test-add of a full reduction (and even
+// the unconditional addition of q of this round's first version) is gone: 32 instructions per lane and round of the
+// permutation.  Every consumer takes such a value: the multiplier and the squarer need a b < q 2^256 (and return fully
+// reduced results), the next linear layer only uses the limbs as 32-bit integers and keeps its bound, and the permutation
+// ends with a product per lane (HADES_UNSCALE), so nothing unreduced leaves it.  The twin checks the range.
 JJS_HD void redc_one(uint32_t* r, const uint32_t* v) {
     uint32_t ev[9], od[9], n[9];
     ev[0] = 0;
@@ -597,26 +573,14 @@ JJS_HD void redc_one(uint32_t* r, const uint32_t* v) {
     for (int i = 0; i < 9; i++) od[i] = 0;
     uint32_t e0;
     redc_step2(ev, od, n, v[8], e0);
-    uint32_t w[8];
-    add8(w, od + 1, n);
-#if JJS_REDC_ONE_LAZY
-    w[7] -= e0;   // mod 2^256; the true value of w - e0 2^224 + q is in (0, q + 2^244)
-    add_q(r, w);
+    add8(r, od + 1, n);
+    r[7] -= e0;   // mod 2^256; the true value is in (0, q + 2^244)
 #if !defined(__CUDA_ARCH__)
-    {   // host twin: 0 <= r < q + 2^244
+    {   // host twin: 0 < r < q + 2^244
         uint32_t t[8], t2[8], lim[8] = {0, 0, 0, 0, 0, 0, 0, 1u << 20};
         uint32_t b = sub_q(t, r);
         if (b == 0 && sub8(t2, t, lim) == 0) jjs_host_bound_violation();
     }
-#endif
-#else
-    // (v + e0 qbar) / 2^32 = r + e0 2^224 with r in (-q, q): take e0 off limb 7, add q back on a borrow
-    uint32_t m[8], d[8];
-#pragma unroll
-    for (int i = 0; i < 7; i++) m[i] = 0;
-    m[7] = e0;
-    uint32_t borrow = sub8(d, w, m);
-    add_q_masked(r, d, borrow);
 #endif
 }
 

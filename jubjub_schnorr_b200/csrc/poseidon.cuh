@@ -29,11 +29,12 @@ JJS_HD void sbox5(fq& x) {
 }
 
 // out = 2^-32 * (ark + sum_k coef[k] * s[k])  mod q
-JJS_HD void mds_lane(fq& out, const fq* s, const uint32_t* ark, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4) {
+// (ark, ark_top): the nine limbs of the round constant plus q 2^32, see redc_one
+JJS_HD void mds_lane(fq& out, const fq* s, const uint32_t* ark, uint32_t ark_top, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4) {
     uint32_t E[9], O[9];
 #pragma unroll
     for (int i = 0; i < 8; i++) { E[i] = ark[i]; O[i] = 0; }
-    E[8] = 0;
+    E[8] = ark_top;
     O[8] = 0;
     const uint32_t coef[5] = {c0, c1, c2, c3, c4};
 #pragma unroll
@@ -47,7 +48,7 @@ JJS_HD void mds_lane(fq& out, const fq* s, const uint32_t* ark, uint32_t c0, uin
     uint32_t v[9];
     v[0] = E[0];
     uint32_t c = add8(v + 1, E + 1, O);
-    (void)c;  // E[8] + O[7] + carry cannot overflow: the sum is < 2^274
+    (void)c;  // E[8] + O[7] + carry cannot overflow: the sum is < 2^288
     redc_one(out.l, v);
 }
 
@@ -78,7 +79,7 @@ JJS_HD uint64_t f64_bits(double d) {
     return b;
 #endif
 }
-JJS_HD void mds_all_fp(fq* o, const fq* s, const uint32_t (*ark)[8]) {
+JJS_HD void mds_all_fp(fq* o, const fq* s, const uint32_t (*ark)[8], const uint32_t* ark_top) {
     // integer Cauchy matrix 360360 / (o + k + 5), indexed by o + k
     const double N[9] = {72072.0, 60060.0, 51480.0, 45045.0, 40040.0, 36036.0, 32760.0, 30030.0, 27720.0};
     uint32_t v[5][9];
@@ -93,14 +94,14 @@ JJS_HD void mds_all_fp(fq* o, const fq* s, const uint32_t (*ark)[8]) {
             double acc = f64_biased_u32(ark[l][i]);
 #pragma unroll
             for (int k = 0; k < 5; k++) acc = fma(N[l + k], d[k], acc);
-            uint64_t t = (f64_bits(acc) & 0x000fffffffffffffull) + carry[l];
+            uint64_t t = f64_bits(acc) - 0x4330000000000000ull + carry[l];   // acc is in [2^52, 2^53): its exponent field is constant
             v[l][i] = (uint32_t)t;
             carry[l] = t >> 32;
         }
     }
 #pragma unroll
     for (int l = 0; l < 5; l++) {
-        v[l][8] = (uint32_t)carry[l];
+        v[l][8] = (uint32_t)carry[l] + ark_top[l];
         redc_one(o[l].l, v[l]);
     }
 }
@@ -135,14 +136,14 @@ JJS_HD void hades_permute(fq* s) {
         }
         fq o[5];
 #if JJS_MDS_FP64
-        mds_all_fp(o, s, JJS_C(HADES_FOLDED_ARK)[rnd]);
+        mds_all_fp(o, s, JJS_C(HADES_FOLDED_ARK)[rnd], JJS_C(HADES_FOLDED_ARK_TOP)[rnd]);
 #else
         // integer Cauchy matrix 360360 / (i + k + 5)
-        mds_lane(o[0], s, JJS_C(HADES_FOLDED_ARK)[rnd][0], 72072u, 60060u, 51480u, 45045u, 40040u);
-        mds_lane(o[1], s, JJS_C(HADES_FOLDED_ARK)[rnd][1], 60060u, 51480u, 45045u, 40040u, 36036u);
-        mds_lane(o[2], s, JJS_C(HADES_FOLDED_ARK)[rnd][2], 51480u, 45045u, 40040u, 36036u, 32760u);
-        mds_lane(o[3], s, JJS_C(HADES_FOLDED_ARK)[rnd][3], 45045u, 40040u, 36036u, 32760u, 30030u);
-        mds_lane(o[4], s, JJS_C(HADES_FOLDED_ARK)[rnd][4], 40040u, 36036u, 32760u, 30030u, 27720u);
+        mds_lane(o[0], s, JJS_C(HADES_FOLDED_ARK)[rnd][0], JJS_C(HADES_FOLDED_ARK_TOP)[rnd][0], 72072u, 60060u, 51480u, 45045u, 40040u);
+        mds_lane(o[1], s, JJS_C(HADES_FOLDED_ARK)[rnd][1], JJS_C(HADES_FOLDED_ARK_TOP)[rnd][1], 60060u, 51480u, 45045u, 40040u, 36036u);
+        mds_lane(o[2], s, JJS_C(HADES_FOLDED_ARK)[rnd][2], JJS_C(HADES_FOLDED_ARK_TOP)[rnd][2], 51480u, 45045u, 40040u, 36036u, 32760u);
+        mds_lane(o[3], s, JJS_C(HADES_FOLDED_ARK)[rnd][3], JJS_C(HADES_FOLDED_ARK_TOP)[rnd][3], 45045u, 40040u, 36036u, 32760u, 30030u);
+        mds_lane(o[4], s, JJS_C(HADES_FOLDED_ARK)[rnd][4], JJS_C(HADES_FOLDED_ARK_TOP)[rnd][4], 40040u, 36036u, 32760u, 30030u, 27720u);
 #endif
 #pragma unroll
         for (int i = 0; i < 5; i++) s[i] = o[i];

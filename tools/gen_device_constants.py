@@ -361,9 +361,11 @@ def main():
     u("#define JJS_DLOG_HASH_BITS %d" % sq["hash_bits"])
     u("#define JJS_MDS_LCM %du" % LCM)
     u("JJS_CONST_QUAL uint32_t HADES_FIRST_ARK[5][8] = {%s};" % ", ".join(limbs(v) for v in sch["first_ark"]))
+    # Emitted as ark + q 2^32 (nine limbs: the low eight here, the ninth in HADES_FOLDED_ARK_TOP at the end of the bank): the
+    # single Montgomery step after a linear layer (csrc/fq.cuh, redc_one) then lands in (0, q + 2^244) without any correction.
     u("JJS_CONST_QUAL uint32_t HADES_FOLDED_ARK[68][5][8] = {")
     for row in sch["folded_ark"]:
-        u(" {" + ", ".join(limbs(v) for v in row) + "},")
+        u(" {" + ", ".join(limbs(v + (Q << 32)) for v in row) + "},")
     u("};")
     u("JJS_CONST_QUAL uint32_t HADES_SBOX_FIX[60][8] = {")
     for v in sch["fixes"]:
@@ -381,6 +383,10 @@ def main():
     inv_sched = window_schedule(Q - 2)
     u("#define JJS_INV_SCHED_LEN %d" % len(inv_sched))
     u("JJS_CONST_QUAL uint8_t INV_SCHED[JJS_INV_SCHED_LEN][2] = {%s}; /* same encoding as SQRT_SCHED, for a^(q-2) */" % ", ".join("{%d, %d}" % s_ for s_ in inv_sched))
+    u("JJS_CONST_QUAL uint32_t HADES_FOLDED_ARK_TOP[68][5] = { /* limb 8 of ark + q 2^32 */")
+    for row in sch["folded_ark"]:
+        u(" {" + ", ".join("0x%08xu" % ((v + (Q << 32)) >> 256) for v in row) + "},")
+    u("};")
     t("/* Large, data-dependently indexed tables: host arrays, uploaded to device global memory at context creation. */")
     t("static const uint8_t DLOG_HASH[1 << %d] = {%s};" % (sq["hash_bits"], ", ".join(map(str, sq["hash_table"]))))
     t("/* root-of-unity tables, Montgomery: T0,T1,T2 = g^(-j 2^(8i)); H1,H2,H3 = g^(-j 2^(8i-1)); order T0,T1,T2,H1,H2,H3 */")
