@@ -11,7 +11,7 @@ with BatchVerifier([0]) as bv:
     dev = torch.device("cuda", 0)
     for it in range(24):
         variant = int(rng.integers(0, 3))
-        n = int(rng.choice([1, 2, 31, 32, 33, 127, 129, 65535, 65537, 262143, 262144, 262145, 300001, 524289, 786433, 1048577]))
+        n = int(rng.choice([1, 2, 31, 32, 33, 127, 129, 65535, 65537, 262143, 262144, 262145, 300001, 524287, 524288, 524289, 786433, 1048577, 131071, 131073]))
         if variant != 0: n = min(n, 600000)
         frac = float(rng.choice([0.0, 0.1, 0.5, 1.0]))
         pk, sig, msg, exp, _ = wl.make_batch(bv, variant, n, frac, seed=1000 + it)
