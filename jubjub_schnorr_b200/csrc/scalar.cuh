@@ -105,22 +105,16 @@ JJS_HD double limbs_to_double(const uint32_t* a) {
     return d;
 }
 
-// Half-size decomposition of a challenge (Antipa, Brown, Gallant, Lambert, Struik, Vanstone: "Accelerated
-// verification of ECDSA signatures"): for c < r returns tau < 2^126 and rho != 0, |rho| < 2^126, with
-//     tau == rho * c  (mod r)            (rho = rho_neg ? -rho_abs : rho_abs)
-// by running the extended Euclidean algorithm on (r, c) until the remainder drops below 2^126.  Then, for points
-// of the prime-order subgroup,  u*G + c*PK == R   <=>   (rho*u)*G + tau*PK - rho*R == O,  which needs 126-bit
-// multipliers for the two variable bases.  Quotients are estimated from below in double precision (the margin
-// 2^-40 dwarfs the 2^-49 conversion error) and capped at 2^31 - 1; the exact comparison a >= b drives the loop, so
-// an underestimate only costs another pass.  Huge quotients are consumed 32 bits at a time.
-//
-// Consecutive cofactors of the Euclidean sequence are coprime, so when the stopping pair has an even rho the pair one
-// step earlier (remainder a >= 2^126, cofactor ta < rho) has an odd one; it is returned instead when its remainder
-// still fits the 33 signed radix-16 digits of the equation kernel (a < 2^130, the usual case: a * rho <= r).  An odd
-// rho is what lets the equation kernel skip the subgroup test of R (verify_core.cuh, stage_equation): rho_odd reports
-// whether one was found.  tau has 5 limbs (< 2^130), rho 4.
-// The Euclidean sequence itself: on return (a, ta) and (b, tb) are consecutive (remainder, cofactor) pairs with b < 2^126 <= a,
+// The classical form of the half-size decomposition (see half_gcd below for what it is for): the extended Euclidean algorithm on
+// (r, c), run until the remainder drops below 2^126.  The kernels use the warp-uniform reduction of half_gcd_vectors; this
+// sequence is its fallback (half_gcd_classical) for a run that does not finish within its round cap, and the reference the
+// twin tests it against.  Quotients are estimated from below in double precision (the margin 2^-40 dwarfs the 2^-49
+// conversion error) and capped at 2^31 - 1; the exact comparison a >= b drives the loop, so an underestimate only costs
+// another pass.  Huge quotients are consumed 32 bits at a time.  On return (a, ta) and (b, tb) are consecutive (remainder,
+// cofactor) pairs with b < 2^126 <= a,
 //     b == (neg ? -tb : tb) * c   and   a == (neg ? ta : -ta) * c   (mod r),        ta <= tb < 2^126.
+// Consecutive cofactors are coprime, so when the stopping pair has an even cofactor the previous pair has an odd one
+// (half_gcd_classical takes it when its remainder still fits the 33 signed radix-16 digits of the equation kernel).
 JJS_HD void half_gcd_core(uint32_t* a, uint32_t* b, uint32_t* ta, uint32_t* tb, bool& neg, const uint32_t* c8) {
 #pragma unroll
     for (int i = 0; i < 4; i++) { ta[i] = 0; tb[i] = 0; }
@@ -184,8 +178,8 @@ JJS_HD void half_gcd_core(uint32_t* a, uint32_t* b, uint32_t* ta, uint32_t* tb, 
 // the triples (x, y, z) form a lattice of rank 3 and determinant r^2, whose short vectors have ~168-bit coordinates
 // (r^(2/3)), and a 3-table Straus interleave over 43 signed radix-16 windows then needs 168 doublings instead of 252.
 //
-// lattice3_reduce finds such a vector.  Basis: the two consecutive pairs (tau_i, rho_i) of the half-gcd of c (126-bit each),
-// extended by x_i = rho_i u mod r, and (r, 0, 0).  Reduction: greedy in the style of Semaev's rank-3 algorithm, with every
+// lattice3_reduce finds such a vector.  Basis: the two reduced vectors (tau_i, rho_i) of the half-size decomposition of c
+// (half_gcd_vectors, ~126 bits each), extended by x_i = rho_i u mod r, and (r, 0, 0).  Reduction: greedy in the style of Semaev's rank-3 algorithm, with every
 // quotient estimated in double precision from 53-bit approximations of the coordinates and applied EXACTLY to the 256-bit
 // integers.  Every update is an integer row operation, so the vectors stay in the lattice whatever the rounding errors
 // do: floating point only steers, it cannot make the result wrong, only longer -- and a result that is too long for the
