@@ -460,9 +460,9 @@ JJS_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi) {  // (hi:lo << 1) >> 32
 // wide products and Montgomery reduction
 // ---------------------------------------------------------------------------------------------
 
-// t[0..15] = a * b (schoolbook, 64 wide multiplies in 16 carry chains over an even and an odd accumulator)
-JJS_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
-    uint32_t E[17], O[15];  // E[k]: limb k;  O[k]: limb k+1
+// a * b as an even and an odd accumulator (schoolbook, 64 wide multiplies in 16 carry chains):
+//     a b = sum_k E[k] 2^(32 k) + sum_k O[k] 2^(32 (k + 1)),   E: 17 limbs, O: 15.
+JJS_HD void mul_wide_eo(uint32_t* E, uint32_t* O, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
     for (int i = 0; i < 17; i++) E[i] = 0;
 #pragma unroll
@@ -483,6 +483,11 @@ JJS_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
         mad_row<4, 1>(O + i, ae, b[i + 1]);
         mad_row<4, 0>(E + i + 2, ao, b[i + 1]);
     }
+}
+// t[0..15] = a * b: the two accumulators merged
+JJS_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+    uint32_t E[17], O[15];  // E[k]: limb k;  O[k]: limb k+1
+    mul_wide_eo(E, O, a, b);
     // t = E + (O << 32)
     t[0] = E[0];
     uint32_t c = add8(t + 1, E + 1, O);
@@ -533,18 +538,13 @@ JJS_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
     mad_diag8(t, a);
 }
 
-// r = t / 2^256 mod q for a 16-limb t < q * 2^256, fully reduced.
-JJS_HD void redc(uint32_t* r, const uint32_t* t) {
-    uint32_t ev[9], od[9], n[9];
-    ev[0] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) ev[i + 1] = t[i];
-#pragma unroll
-    for (int i = 0; i < 9; i++) od[i] = 0;
-    uint32_t M[8];
+// The eight reduction steps and the final correction, from a state (ev, od) that holds T 2^32 (ev[0] == 0) and the eight high
+// limbs of T still to be injected, hi[i] at weight 2^(32 (8 + i)): r = T / 2^256 mod q, fully reduced, for T < q 2^256.
+JJS_HD void redc_run(uint32_t* r, uint32_t* ev, uint32_t* od, const uint32_t* hi) {
+    uint32_t n[9], M[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        redc_step2(ev, od, n, t[8 + i], M[i]);
+        redc_step2(ev, od, n, hi[i], M[i]);
 #pragma unroll
         for (int k = 0; k < 9; k++) { ev[k] = od[k]; od[k] = n[k]; }
     }
@@ -554,7 +554,42 @@ JJS_HD void redc(uint32_t* r, const uint32_t* t) {
     uint32_t borrow = sub8(d, v, M);
     add_q_masked(r, d, borrow);
 }
-
+// r = t / 2^256 mod q for a 16-limb t < q * 2^256, fully reduced.
+JJS_HD void redc(uint32_t* r, const uint32_t* t) {
+    uint32_t ev[9], od[9];
+    ev[0] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ev[i + 1] = t[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) od[i] = 0;
+    redc_run(r, ev, od, t + 8);
+}
+// The same for a product still held as an even and an odd accumulator (mul_wide_eo).  The reduction state is itself a pair
+// of limb vectors offset by one limb, and every step treats it as such (the quotient digit is formed from od[0] + ev[1], all
+// carries stay inside the step's two chains and are captured in the top limbs), so the LOW halves of E and O go in
+// unmerged -- T 2^32 = sum E[k] 2^(32 (k + 1)) + sum O[k] 2^(32 (k + 2)): od = (E[0..7], 0), ev = (0, 0, O[0..6]) -- and only the
+// high halves are merged, into the eight limbs that the steps inject: hi[i] = E[8 + i] + O[7 + i] + carry.  The value the
+// state stands for is the same as in redc at every step, so the bounds that let the last addition drop od[8] and its carry
+// hold unchanged; what is saved is the merge of the low halves (nine instructions per product).
+JJS_HD void redc_eo(uint32_t* r, const uint32_t* E, const uint32_t* O) {
+    uint32_t ev[9], od[9], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) od[i] = E[i];      // E[k] at 2^(32 (k + 1)) is od[k]: the accumulators keep their register pairs
+    od[8] = 0;
+    ev[0] = 0;
+    ev[1] = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) ev[i + 2] = O[i];  // O[k] at 2^(32 (k + 2)) is ev[k + 2]
+    uint32_t x[8] = {E[8], E[9], E[10], E[11], E[12], E[13], E[14], E[15]};
+    uint32_t y[8] = {O[7], O[8], O[9], O[10], O[11], O[12], O[13], O[14]};
+    uint32_t c = add8(hi, x, y);   // limbs 8..15 of the product, less the carry the unmerged low halves still owe
+#if !defined(__CUDA_ARCH__)
+    if (c != 0u || E[16] != 0u) jjs_host_bound_violation();   // a b < 2^512: nothing reaches limb 16
+#else
+    (void)c;
+#endif
+    redc_run(r, ev, od, hi);
+}
 // One Montgomery step after the small-integer linear maps of the hash, without any correction: for a 9-limb
 //     v' = v + q 2^32,   v < 2^20 q   (the caller's constants carry the q 2^32: HADES_FOLDED_ARK is emitted that way)
 // returns r == v / 2^32 (mod q) with 0 < r < q + 2^244 -- ALMOST reduced.  With e0 the quotient digit (it only depends on the low
@@ -587,10 +622,19 @@ JJS_HD void redc_one(uint32_t* r, const uint32_t* v) {
 // ---------------------------------------------------------------------------------------------
 // field API (all values fully reduced, Montgomery form unless stated)
 // ---------------------------------------------------------------------------------------------
+#ifndef JJS_REDC_EO
+#define JJS_REDC_EO 1   // reduce the product from its two accumulators without merging their low halves
+#endif
 JJS_HD void fq_mul_inl(fq& r, const fq& a, const fq& b) {
+#if JJS_REDC_EO
+    uint32_t E[17], O[15];
+    mul_wide_eo(E, O, a.l, b.l);
+    redc_eo(r.l, E, O);
+#else
     uint32_t t[16];
     mul_wide(t, a.l, b.l);
     redc(r.l, t);
+#endif
 }
 JJS_HD void fq_sqr_inl(fq& r, const fq& a) {
     uint32_t t[16];
