@@ -59,6 +59,28 @@ def test_adversarial_batch_matches_oracle(bv, kind, n):
     assert set(st_g.tolist()) == {0, 1, 2, 3}
 
 
+SPECIAL_U = [0, 1, 2, 7, 8, o.R_ORDER - 1, o.R_ORDER - 2, o.R_ORDER // 2, o.R_ORDER // 3, 1 << 84, 1 << 126, (1 << 126) - 1, 1 << 127, 1 << 168,
+             (1 << 170) - 1, 1 << 250, (1 << 251) + 12345]
+
+
+@pytest.mark.parametrize("kind", ["single", "double", "vargen"])
+def test_special_response_scalars(bv, kind):
+    """Response scalars u at the edges of the scalar decompositions (0, 1, r - 1, powers of two around the half-size and the
+    three-scalar bounds) in otherwise valid items: the equation must simply fail, exactly as in the oracle, next to untouched
+    valid items in the same warps."""
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    cver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    gver = {"single": bv.verify_single, "double": bv.verify_double, "vargen": bv.verify_vargen}[kind]
+    n = 4 * len(SPECIAL_U)
+    pk, sig, msg = gen(0xB207, n)
+    for j, u in enumerate(SPECIAL_U):
+        sig[4 * j, :32] = np.frombuffer(u.to_bytes(32, "little"), dtype=np.uint8)
+    st_o, c_o = cver(pk, sig, msg)
+    st_g, c_g = gver(pk, sig, msg, True)
+    assert (st_o[0::4] == 1).all() and not st_o[1::4].any()
+    assert np.array_equal(st_g, st_o) and np.array_equal(c_g, c_o)
+
+
 @pytest.mark.parametrize("kind", ["single", "double", "vargen"])
 def test_torsion_shifted_signatures_are_invalid_points(bv, kind):
     """R = r*B + T (T of order 2, 4, 8) signed by the key holder: the equation holds up to torsion, so only the

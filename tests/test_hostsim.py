@@ -190,6 +190,23 @@ def test_pipeline_twin_on_adversarial_batches(L, vi, kind, impl):
     assert np.array_equal(hc, c) and np.array_equal(st, exp)
 
 
+@pytest.mark.parametrize("vi,kind", [(0, "single"), (1, "double"), (2, "vargen")])
+def test_special_response_scalars_twin(L, vi, kind):
+    """u at the edges of the scalar decompositions in otherwise valid items (the GPU test of the same name, on the twin)."""
+    special = [0, 1, 2, 7, 8, o.R_ORDER - 1, o.R_ORDER - 2, o.R_ORDER // 2, 1 << 84, 1 << 126, (1 << 126) - 1, 1 << 127, 1 << 168, (1 << 170) - 1, 1 << 250]
+    gen = {"single": co.gen_single, "double": co.gen_double, "vargen": co.gen_vargen}[kind]
+    ver = {"single": co.verify_single, "double": co.verify_double, "vargen": co.verify_vargen}[kind]
+    n = 2 * len(special)
+    pk, sig, msg = gen(0xB207, n)
+    for j, u in enumerate(special):
+        sig[2 * j, :32] = np.frombuffer(u.to_bytes(32, "little"), dtype=np.uint8)
+    st, c = ver(pk, sig, msg)
+    hst, hc = np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8)
+    L.hs_verify(vi, _p(pk), _p(sig), _p(msg), C.c_size_t(n), _p(hst), _p(hc))
+    assert (st[0::2] == 1).all() and not st[1::2].any()
+    assert np.array_equal(hst, st) and np.array_equal(hc, c)
+
+
 def test_vargen_fallback_when_no_short_vector_is_found(L):
     """The var-generator equation falls back to the two-table evaluation when the lattice reduction reports no vector that fits
     its windows (unreachable with hash outputs, so the twin forces it): same statuses and challenges."""
