@@ -345,7 +345,7 @@ constexpr int AGG_GROUP = 4;  // signer keys folded per shared doubling chain (p
 // acc += sum_{j in [j0, j1)} d_j * pk_j,  j1 - j0 <= AGG_GROUP;  optionally stores the coefficients d_j (8 words each)
 // `d_ready`: the coefficients were computed by an earlier kernel (stage_aggregate_coeffs) and are read from d_words
 JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j0, uint32_t j1, uint32_t* d_words,
-                            fq* tab, size_t stride, const fq* tags, bool d_ready = false) {
+                            fq* tab, size_t stride, const fq* tags, bool d_ready = false, bool first_group = false) {
     int8_t digits[AGG_GROUP][64];
     int nb = 0;
 #pragma unroll 1
@@ -363,6 +363,10 @@ JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32
     }
     ext term, sum;
     straus_multi(term, nb, tab, stride, digits);
+    if (first_group) {   // nothing to add it to yet (the usual case: at most AGG_GROUP signers)
+        acc = term;
+        return;
+    }
     pniels nt;
     ext_to_pniels(nt, term);
     ext_add_pniels<true>(sum, acc, nt);
@@ -413,7 +417,7 @@ JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* k
     ext_identity(acc);
 #pragma unroll 1
     for (uint32_t j = lo; j < hi; j += AGG_GROUP)
-        aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tab, stride, tags, d_words != nullptr);
+        aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tab, stride, tags, d_words != nullptr, j == lo);
     fq zi, u, v, one;
     fq_inv(zi, acc.Z);
     fq_mul(u, acc.X, zi);
