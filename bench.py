@@ -442,7 +442,9 @@ def main():
     traffic = None
     try:  # DRAM bytes of the dominant kernel per step, from the committed ncu capture (bytes per unit x units in this step)
         traffic_file = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))[-1]   # newest capture
-        tr = json.load(open(traffic_file))["kernels"]["k_" + dom]
+        trk = json.load(open(traffic_file))["kernels"]
+        vg_only = dom == "equation" and all(p.kind == "vargen" for p in shards[0])   # the var-generator equation kernel has its own capture
+        tr = trk["k_equation_vargen"] if vg_only and "k_equation_vargen" in trk else trk["k_" + dom]
         traffic = tr["dram_bytes_per_unit"] * {"decode": units["decode"], "challenge": sum(p.n for p in shards[0]),
                                                "equation": sum(p.n * NEQ.get(p.kind, 1) for p in shards[0]), "aggregate": units["aggregate"]}[dom]
     except Exception:
