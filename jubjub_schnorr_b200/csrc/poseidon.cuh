@@ -79,7 +79,10 @@ JJS_HD uint64_t f64_bits(double d) {
     return b;
 #endif
 }
-JJS_HD void mds_all_fp(fq* o, const fq* s, const uint32_t (*ark)[8], const uint32_t* ark_top) {
+#ifndef JJS_MDS_CVT
+#define JJS_MDS_CVT 1   // lift the limbs with the conversion instruction (0: the bias trick 2^52 + x, two more moves per limb)
+#endif
+JJS_HD void mds_all_fp(fq* o, const fq* s, const double (*arkd)[8], const uint32_t* ark_top) {
     // integer Cauchy matrix 360360 / (o + k + 5), indexed by o + k
     const double N[9] = {72072.0, 60060.0, 51480.0, 45045.0, 40040.0, 36036.0, 32760.0, 30030.0, 27720.0};
     uint32_t v[5][9];
@@ -88,10 +91,14 @@ JJS_HD void mds_all_fp(fq* o, const fq* s, const uint32_t (*ark)[8], const uint3
     for (int i = 0; i < 8; i++) {
         double d[5];
 #pragma unroll
+#if JJS_MDS_CVT
+        for (int k = 0; k < 5; k++) d[k] = (double)s[k].l[i];
+#else
         for (int k = 0; k < 5; k++) d[k] = f64_biased_u32(s[k].l[i]) - 4503599627370496.0;
+#endif
 #pragma unroll
         for (int l = 0; l < 5; l++) {
-            double acc = f64_biased_u32(ark[l][i]);
+            double acc = arkd[l][i];   // 2^52 + limb i of the round constant, straight from the constant bank
 #pragma unroll
             for (int k = 0; k < 5; k++) acc = fma(N[l + k], d[k], acc);
             uint64_t t = f64_bits(acc) - 0x4330000000000000ull + carry[l];   // acc is in [2^52, 2^53): its exponent field is constant
@@ -136,7 +143,7 @@ JJS_HD void hades_permute(fq* s) {
         }
         fq o[5];
 #if JJS_MDS_FP64
-        mds_all_fp(o, s, JJS_C(HADES_FOLDED_ARK)[rnd], JJS_C(HADES_FOLDED_ARK_TOP)[rnd]);
+        mds_all_fp(o, s, JJS_C(HADES_FOLDED_ARK_D)[rnd], JJS_C(HADES_FOLDED_ARK_TOP)[rnd]);
 #else
         // integer Cauchy matrix 360360 / (i + k + 5)
         mds_lane(o[0], s, JJS_C(HADES_FOLDED_ARK)[rnd][0], JJS_C(HADES_FOLDED_ARK_TOP)[rnd][0], 72072u, 60060u, 51480u, 45045u, 40040u);

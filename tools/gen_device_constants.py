@@ -383,6 +383,11 @@ def main():
     inv_sched = window_schedule(Q - 2)
     u("#define JJS_INV_SCHED_LEN %d" % len(inv_sched))
     u("JJS_CONST_QUAL uint8_t INV_SCHED[JJS_INV_SCHED_LEN][2] = {%s}; /* same encoding as SQRT_SCHED, for a^(q-2) */" % ", ".join("{%d, %d}" % s_ for s_ in inv_sched))
+    u("/* the same limbs as doubles 2^52 + limb: the FP64 linear layer starts its exact column sums from them */")
+    u("JJS_CONST_QUAL double HADES_FOLDED_ARK_D[68][5][8] = {")
+    for row in sch["folded_ark"]:
+        u(" {" + ", ".join("{" + ", ".join("%d.0" % ((1 << 52) + (((v + (Q << 32)) >> (32 * i)) & 0xFFFFFFFF)) for i in range(8)) + "}" for v in row) + "},")
+    u("};")
     u("JJS_CONST_QUAL uint32_t HADES_FOLDED_ARK_TOP[68][5] = { /* limb 8 of ark + q 2^32 */")
     for row in sch["folded_ark"]:
         u(" {" + ", ".join("0x%08xu" % ((v + (Q << 32)) >> 256) for v in row) + "},")
