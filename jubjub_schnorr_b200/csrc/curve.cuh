@@ -225,8 +225,7 @@ JJS_HD void fq_pow_sched(fq& r, const fq& a) {
 #pragma unroll 1
     for (int s = 1; s < LEN; s++) {
         int nsq = pow_sched_entry<WHICH>(s, 0), idx = pow_sched_entry<WHICH>(s, 1);
-#pragma unroll 1
-        for (int k = 0; k < nsq; k++) fq_sqr(acc, acc);
+        fq_sqr_n(acc, acc, nsq);
         if (idx != 0xff) fq_mul(acc, acc, odd[idx]);
     }
     r = acc;
@@ -269,14 +268,11 @@ JJS_HD bool fq_sqrt_ratio(fq& r, const fq& num, const fq& den, const Tables& T) 
     fq_sqr(b, w);
     fq_mul(b, b, a);
     p1 = b;
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) fq_sqr(p1, p1);
+    fq_sqr_n(p1, p1, 8);
     p2 = p1;
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) fq_sqr(p2, p2);
+    fq_sqr_n(p2, p2, 8);
     p3 = p2;
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) fq_sqr(p3, p3);
+    fq_sqr_n(p3, p3, 8);
     uint32_t k0 = dlog8(T, p3);
     root_table_load(t, T, 2, k0);      // g^(-k0 2^16)
     fq_mul(x, p2, t);
@@ -694,8 +690,7 @@ JJS_HD bool point_is_torsion_free_tate(const fq& u, const fq& v) {
     fq_pow_tm1d2(w, g);
     fq_sqr(w, w);
     fq_mul(w, w, g);
-#pragma unroll 1
-    for (int i = 0; i < 29; i++) fq_sqr(w, w);
+    fq_sqr_n(w, w, 29);
     return fq_eq(w, one);
 }
 

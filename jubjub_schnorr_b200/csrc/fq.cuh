@@ -657,9 +657,33 @@ __device__ __noinline__ fq fq_sqr_fn(fq a) {
 }
 JJS_HD void fq_mul(fq& r, const fq& a, const fq& b) { r = fq_mul_fn(a, b); }
 JJS_HD void fq_sqr(fq& r, const fq& a) { r = fq_sqr_fn(a); }
+// a^(2^n): the loop lives INSIDE the callee.  A chain of calls `x = sqr(x)` costs ~16 moves per squaring, because the caller
+// keeps x in other registers than the callee's arguments; the fixed exponentiations of the square root, the subgroup test and
+// the inversion are ~90 % such chains (-DJJS_SQR_CHAIN=0: a loop of calls).
+#ifndef JJS_SQR_CHAIN
+#define JJS_SQR_CHAIN 1
+#endif
+__device__ __noinline__ fq fq_sqr_n_fn(fq a, int n) {
+#pragma unroll 1
+    for (int k = 0; k < n; k++) fq_sqr_inl(a, a);
+    return a;
+}
+JJS_HD void fq_sqr_n(fq& r, const fq& a, int n) {
+#if JJS_SQR_CHAIN
+    r = fq_sqr_n_fn(a, n);
+#else
+    r = a;
+#pragma unroll 1
+    for (int k = 0; k < n; k++) r = fq_sqr_fn(r);
+#endif
+}
 #else
 JJS_HD void fq_mul(fq& r, const fq& a, const fq& b) { fq_mul_inl(r, a, b); }
 JJS_HD void fq_sqr(fq& r, const fq& a) { fq_sqr_inl(r, a); }
+JJS_HD void fq_sqr_n(fq& r, const fq& a, int n) {
+    r = a;
+    for (int k = 0; k < n; k++) fq_sqr_inl(r, r);
+}
 #endif
 JJS_HD void fq_add(fq& r, const fq& a, const fq& b) {
     uint32_t v[8], s[8];
