@@ -411,9 +411,7 @@ JJS_HD void varbase_table_build_ext(fq* tab, size_t stride, const ext& p) {
     acc = p;
 #pragma unroll 1
     for (int k = 2; k <= 8; k++) {
-        ext nx;
-        ext_add_pniels<true>(nx, acc, n1);
-        acc = nx;
+        ext_add_pniels<true>(acc, acc, n1);   // in place
         ext_to_pniels(n, acc);
         pniels_store(tab, stride, k, n);
     }
@@ -522,9 +520,9 @@ JJS_HD void straus_multi(ext& r, int nb, const fq* tab, size_t stride, const int
             int d = digits[b][i];
             pniels_load(n, tab + (size_t)b * 36 * stride, stride, d < 0 ? -d : d);
             pniels_cneg(n, d < 0);
-            if (b == nb - 1 && i != 0) ext_add_pniels<false>(t, acc, n);
-            else ext_add_pniels<true>(t, acc, n);
-            acc = t;
+            // in place: the addition reads all of its first operand before it writes the result
+            if (b == nb - 1 && i != 0) ext_add_pniels<false>(acc, acc, n);
+            else ext_add_pniels<true>(acc, acc, n);
         }
     }
     r = acc;
@@ -558,9 +556,7 @@ JJS_HD void fixedbase_acc(ext& acc, const niels* table, const uint32_t* k) {
         if ((bit & 31) + FB_W > 32 && (bit >> 5) + 1 < 8) lo |= k[(bit >> 5) + 1] << (32 - (bit & 31));
         uint32_t idx = lo & (FB_ENTRIES - 1);
         niels n = table[(size_t)w * FB_ENTRIES + idx];
-        ext t;
-        ext_add_niels<true>(t, acc, n);
-        acc = t;
+        ext_add_niels<true>(acc, acc, n);   // in place
     }
 }
 
