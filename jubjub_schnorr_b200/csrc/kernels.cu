@@ -1432,7 +1432,11 @@ int init_device(jjs_ctx* ctx, DeviceState& d) {
         static_assert((1 << FB_LO) % FB_BATCH == 0, "a batch of table entries must share its high half");
         fq *small_u = nullptr, *small_v = nullptr;
         JJS_CUDA(ctx, cudaMalloc(&small_u, sizeof(fq) * FB_WINDOWS * FB_SMALL));
-        JJS_CUDA(ctx, cudaMalloc(&small_v, sizeof(fq) * FB_WINDOWS * FB_SMALL));
+        {
+            cudaError_t em = cudaMalloc(&small_v, sizeof(fq) * FB_WINDOWS * FB_SMALL);
+            if (em != cudaSuccess) cudaFree(small_u);
+            JJS_CUDA(ctx, em);
+        }
         for (int which = 0; which < 2; which++) {
             k_fb_small<<<blocks_for(FB_WINDOWS * FB_SMALL), BLOCK, 0, d.stream>>>(small_u, small_v, which);
             k_fb_combine<<<blocks_for((size_t)FB_WINDOWS * FB_ENTRIES / FB_BATCH), BLOCK, 0, d.stream>>>(which ? d.fb_gn : d.fb_g, small_u, small_v);
