@@ -465,6 +465,7 @@ JJS_HD void varbase_mul(ext& r, const fq* tab, size_t stride, const DIGITS& digi
 #if JJS_ROLL_DBL
 #define JJS_DBL4(acc, t)                                                \
     do {                                                                \
+        (void)(t);                                                      \
         _Pragma("unroll 1") for (int k_ = 0; k_ < 3; k_++) ext_dbl<false>(acc, acc); \
         ext_dbl<true>(acc, acc);                                        \
     } while (0)
