@@ -401,7 +401,8 @@ JJS_HD void pniels_load(pniels& n, const fq* tab, size_t stride, int entry) {
     n.z2 = p[2 * stride];
     n.t2d = p[3 * stride];
 }
-JJS_HD void varbase_table_build_ext(fq* tab, size_t stride, const ext& p) {
+// entries 0 .. nent of the table: multiples 0, 1, .., nent of p (nent = 8 for radix-16 digits, 16 for radix-32)
+JJS_HD void varbase_table_build_ext(fq* tab, size_t stride, const ext& p, int nent = 8) {
     ext acc;
     pniels n1, n;
     pniels_identity(n);
@@ -410,16 +411,16 @@ JJS_HD void varbase_table_build_ext(fq* tab, size_t stride, const ext& p) {
     pniels_store(tab, stride, 1, n1);
     acc = p;
 #pragma unroll 1
-    for (int k = 2; k <= 8; k++) {
+    for (int k = 2; k <= nent; k++) {
         ext_add_pniels<true>(acc, acc, n1);   // in place
         ext_to_pniels(n, acc);
         pniels_store(tab, stride, k, n);
     }
 }
-JJS_HD void varbase_table_build(fq* tab, size_t stride, const fq& u, const fq& v) {
+JJS_HD void varbase_table_build(fq* tab, size_t stride, const fq& u, const fq& v, int nent = 8) {
     ext p;
     ext_from_affine(p, u, v);
-    varbase_table_build_ext(tab, stride, p);
+    varbase_table_build_ext(tab, stride, p, nent);
 }
 // acc = 16 * acc + digit * P, digit in [-8, 8], P's multiples in `tab`
 template <bool WANT_T>
@@ -522,6 +523,51 @@ JJS_HD void straus_multi(ext& r, int nb, const fq* tab, size_t stride, const int
             pniels_load(n, tab + (size_t)b * 36 * stride, stride, d < 0 ? -d : d);
             pniels_cneg(n, d < 0);
             // in place: the addition reads all of its first operand before it writes the result
+            if (b == nb - 1 && i != 0) ext_add_pniels<false>(acc, acc, n);
+            else ext_add_pniels<true>(acc, acc, n);
+        }
+    }
+    r = acc;
+}
+
+// ---- radix-32 variant for full-size scalars on several bases (key aggregation) ---------------------------------------------------
+// With 250-bit coefficients and up to four bases per doubling chain, 5-bit windows beat 4-bit ones: 51 windows instead of 63
+// (13 additions less per base) for eight more table entries per base (72 products): -43 products per base.
+constexpr int R32_DIGITS = 52;          // signed radix-32 digits d_i in [-16, 16) of a 256-bit scalar; index 51 is only a carry
+constexpr int R32_TAB_FQ = 17 * 4;      // entries 0..16 of a per-thread table, four field elements each
+JJS_HD void recode_signed32(int8_t* digits, const uint32_t* k) {
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < R32_DIGITS; i++) {
+        int bit = 5 * i;
+        uint32_t w = 0;
+        if (bit < 256) {
+            w = k[bit >> 5] >> (bit & 31);
+            if ((bit & 31) > 27 && (bit >> 5) + 1 < 8) w |= k[(bit >> 5) + 1] << (32 - (bit & 31));
+        }
+        int d = (int)(w & 31u) + (int)carry;
+        carry = d >= 16;
+        digits[i] = (int8_t)(d - (int)(carry << 5));
+    }
+}
+// acc = sum_b sum_i 32^i d[b][i] * P_b for nb <= 4 bases sharing one doubling chain over `nd` radix-32 digits; table b (entries
+// 0..16, varbase_table_build with nent = 16) lives at tab + b * R32_TAB_FQ * stride.  acc.T is defined on return.
+JJS_HD void straus_multi32(ext& r, int nb, const fq* tab, size_t stride, const int8_t (*digits)[R32_DIGITS], int nd) {
+    ext acc;
+    pniels n;
+    ext_identity(acc);
+#pragma unroll 1
+    for (int i = nd - 1; i >= 0; i--) {
+        if (i != nd - 1) {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) ext_dbl<false>(acc, acc);
+            ext_dbl<true>(acc, acc);
+        }
+#pragma unroll 1
+        for (int b = 0; b < nb; b++) {
+            int d = digits[b][i];
+            pniels_load(n, tab + (size_t)b * R32_TAB_FQ * stride, stride, d < 0 ? -d : d);
+            pniels_cneg(n, d < 0);
             if (b == nb - 1 && i != 0) ext_add_pniels<false>(acc, acc, n);
             else ext_add_pniels<true>(acc, acc, n);
         }

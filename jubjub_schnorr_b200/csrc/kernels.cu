@@ -679,7 +679,7 @@ int ensure_scratch(jjs_ctx* ctx, DeviceState& d) {
     JJS_CUDA(ctx, cudaMalloc(&d.rlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
     JJS_CUDA(ctx, cudaMalloc(&d.rcount, 8 * sizeof(uint32_t)));
     JJS_CUDA(ctx, cudaMalloc(&d.eqlist, sizeof(uint32_t) * 2 * CHUNK_ITEMS));
-    JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * AGG_GROUP * 36 * TAB_THREADS));
+    JJS_CUDA(ctx, cudaMalloc(&d.tab, sizeof(fq) * AGG_GROUP * R32_TAB_FQ * TAB_THREADS));   // the key-aggregation kernel's four tables per thread
     {
         cudaDeviceProp prop;
         JJS_CUDA(ctx, cudaGetDeviceProperties(&prop, d.device));

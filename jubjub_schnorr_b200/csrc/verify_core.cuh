@@ -340,13 +340,14 @@ JJS_HD void aggregate_coeff_words(uint32_t* d, const fq* keys_u, const fq* keys_
     sponge_squeeze_truncated(d, sp);
 }
 
-constexpr int AGG_GROUP = 4;  // signer keys folded per shared doubling chain (per-thread tables: AGG_GROUP x 1152 B)
+constexpr int AGG_GROUP = 4;  // signer keys folded per shared doubling chain (per-thread tables: AGG_GROUP x R32_TAB_FQ field elements)
+constexpr int AGG_DIGITS = 51;  // radix-32 digits of a coefficient below 2^250 (the 51st is at most a carry)
 
 // acc += sum_{j in [j0, j1)} d_j * pk_j,  j1 - j0 <= AGG_GROUP;  optionally stores the coefficients d_j (8 words each)
 // `d_ready`: the coefficients were computed by an earlier kernel (stage_aggregate_coeffs) and are read from d_words
 JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32_t lo, uint32_t hi, uint32_t j0, uint32_t j1, uint32_t* d_words,
                             fq* tab, size_t stride, const fq* tags, bool d_ready = false, bool first_group = false) {
-    int8_t digits[AGG_GROUP][64];
+    int8_t digits[AGG_GROUP][R32_DIGITS];
     int nb = 0;
 #pragma unroll 1
     for (uint32_t j = j0; j < j1; j++, nb++) {
@@ -358,11 +359,11 @@ JJS_HD void aggregate_group(ext& acc, const fq* keys_u, const fq* keys_v, uint32
             if (d_words)
                 for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
         }
-        recode_signed16(digits[nb], d);
-        varbase_table_build(tab + (size_t)nb * 36 * stride, stride, keys_u[j], keys_v[j]);
+        recode_signed32(digits[nb], d);
+        varbase_table_build(tab + (size_t)nb * R32_TAB_FQ * stride, stride, keys_u[j], keys_v[j], 16);
     }
     ext term, sum;
-    straus_multi(term, nb, tab, stride, digits);
+    straus_multi32(term, nb, tab, stride, digits, AGG_DIGITS);
     if (first_group) {   // nothing to add it to yet (the usual case: at most AGG_GROUP signers)
         acc = term;
         return;
@@ -404,22 +405,27 @@ JJS_HD void stage_aggregate_coeff_key(const fq* keys_u, const fq* keys_v, const 
     for (int i = 0; i < 8; i++) d_words[8 * (size_t)j + i] = d[i];
 }
 
+// The aggregation in two halves around the inversion (sharing one inversion between two items of a thread was measured: no
+// gain, the second accumulator spills).  First half: acc = sum_j d_j pk_j in extended coordinates; returns false (acc untouched) if a signer key did not decode.
 // d_words: nullptr (coefficients are hashed here) or the output of stage_aggregate_coeffs for the same keys
-JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
-                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride, const fq* tags, uint32_t* d_words = nullptr) {
-    if (!aggregate_ready(kflags, lo, hi)) {
+JJS_HD bool stage_aggregate_point(ext& acc, const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* tab, size_t stride,
+                                  const fq* tags, uint32_t* d_words) {
+    if (!aggregate_ready(kflags, lo, hi)) return false;
+    ext_identity(acc);
+#pragma unroll 1
+    for (uint32_t j = lo; j < hi; j += AGG_GROUP)
+        aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tab, stride, tags, d_words != nullptr, j == lo);
+    return true;
+}
+// Second half: affine coordinates from acc and zi = 1 / acc.Z, validity flags, wire encoding (all zero if the keys were not ready)
+JJS_HD void stage_aggregate_finish(bool ready, const ext& acc, const fq& zi, fq* out_u, fq* out_v, uint8_t* out_flags, size_t out_index, uint32_t* agg_wire) {
+    if (!ready) {
         out_flags[out_index] = 0;
         if (agg_wire)
             for (int i = 0; i < 8; i++) agg_wire[i] = 0;
         return;
     }
-    ext acc;
-    ext_identity(acc);
-#pragma unroll 1
-    for (uint32_t j = lo; j < hi; j += AGG_GROUP)
-        aggregate_group(acc, keys_u, keys_v, lo, hi, j, j + AGG_GROUP < hi ? j + AGG_GROUP : hi, d_words, tab, stride, tags, d_words != nullptr, j == lo);
-    fq zi, u, v, one;
-    fq_inv(zi, acc.Z);
+    fq u, v, one;
     fq_mul(u, acc.X, zi);
     fq_mul(v, acc.Y, zi);
     fq_one(one);
@@ -430,7 +436,15 @@ JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* k
     out_flags[out_index] = fl;
     if (agg_wire) point_to_wire(agg_wire, u, v);
 }
-
+JJS_HD void stage_aggregate(const fq* keys_u, const fq* keys_v, const uint8_t* kflags, uint32_t lo, uint32_t hi, fq* out_u, fq* out_v,
+                            uint8_t* out_flags, size_t out_index, uint32_t* agg_wire, fq* tab, size_t stride, const fq* tags, uint32_t* d_words = nullptr) {
+    ext acc;
+    bool ready = stage_aggregate_point(acc, keys_u, keys_v, kflags, lo, hi, tab, stride, tags, d_words);
+    fq zi;
+    if (ready) fq_inv(zi, acc.Z);
+    else fq_zero(zi);
+    stage_aggregate_finish(ready, acc, zi, out_u, out_v, out_flags, out_index, agg_wire);
+}
 // ---- stage 5: combine flags into the reference's result -----------------------------------------
 JJS_HD uint8_t stage_status(int variant, const uint8_t* pflags, uint8_t item_flags, size_t n, size_t item) {
     const int slots = variant_slots(variant);

@@ -198,7 +198,7 @@ void hs_verify_aggregate(const uint8_t* pks, const uint32_t* offsets, const uint
                          uint8_t* c_out, uint8_t* agg_out) {
     ensure_ready();
     size_t K = offsets[n];
-    std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(36 * AGG_GROUP);
+    std::vector<fq> ku(K), kv(K), pu(2 * n), pv(2 * n), tab(R32_TAB_FQ * AGG_GROUP);
     std::vector<uint8_t> kf(K), pf(2 * n), itf(n);
     std::vector<uint32_t> cw(8 * n), kc(8 * K + 8);
     WireField fk{pks, 32}, fR{sig + 32, 64}, fmsg{msg, 32}, fu{sig, 64};
@@ -289,7 +289,7 @@ void hs_multisig_combine(const uint8_t* pks, const uint8_t* Rs, const uint8_t* S
                          uint8_t* share_ok, uint8_t* status, uint32_t* bad, uint8_t* sig) {
     ensure_ready();
     size_t K = offsets[n];
-    std::vector<fq> pu(3 * K + 1), pv(3 * K + 1), tab(36 * AGG_GROUP), ru(n), rv(n);
+    std::vector<fq> pu(3 * K + 1), pv(3 * K + 1), tab(R32_TAB_FQ * AGG_GROUP), ru(n), rv(n);
     std::vector<uint8_t> pf(3 * K + 1), sf(n);
     std::vector<uint32_t> dw(8 * K + 8), cdw(8 * K + 8), aw(8 * n);
     WireField f[3] = {{pks, 32}, {Rs, 32}, {Ss, 32}}, fmsg{msg, 32}, fz{zs, 32};
