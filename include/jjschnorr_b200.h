@@ -56,7 +56,7 @@ typedef struct jjs_ctx jjs_ctx;
 /* Create a context over the given CUDA device ordinals (n_devices >= 1; devices == NULL means device 0
  * .. n_devices-1).  Builds the per-device constant tables -- among them the fixed-base window tables for the two generators,
  * 2.4 GB each (12 windows of 2^21 points; ~70 ms per device) -- and allocates no batch memory yet; the first verification adds
- * ~5.3 GiB of scratch per device (sized for 2^20 items in flight, whatever the batch size).
+ * ~9.3 GiB of scratch per device (sized for 2^20 items in flight, whatever the batch size).
  * On failure *out still receives a context, for jjs_last_error only: every other entry point returns JJS_ERR_CUDA on
  * it (there is no CPU fallback) and jjs_destroy frees it. */
 int jjs_init(const int* devices, int n_devices, jjs_ctx** out);
